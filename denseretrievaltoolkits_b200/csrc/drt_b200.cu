@@ -1,0 +1,607 @@
+// drt_b200.cu — C ABI (include/drt_b200.h) and host-side orchestration of the B200 exact-MIPS
+// hot path.  Device code lives in the .cuh files next to this one.  sm_100a only; every entry
+// point fails with an error (never a CPU fallback) when no such device is present.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/drt_b200.h"
+#include "inbatch_ce.cuh"
+#include "mips_filter.cuh"
+#include "select_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                      \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess) {                                                            \
+            (void)cudaGetLastError();                                                       \
+            return fail(_e == cudaErrorMemoryAllocation ? DRT_E_OOM : DRT_E_CUDA,           \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                        __LINE__);                                                          \
+        }                                                                                   \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; (void)cudaGetLastError(); }
+        ok = cudaSetDevice(dev) == cudaSuccess;
+        if (!ok) (void)cudaGetLastError();
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+int check_device(int device) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
+        (void)cudaGetLastError();
+        return fail(DRT_E_NO_DEVICE, "no CUDA device available: this library has no CPU fallback");
+    }
+    if (device < 0 || device >= n) return fail(DRT_E_INVALID, "device %d out of range [0,%d)", device, n);
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device);
+    if (major != 10)
+        return fail(DRT_E_NO_DEVICE, "device %d is sm_%d0, need sm_100 (B200): no fallback path", device, major);
+    return DRT_OK;
+}
+
+// ---- TMA descriptor creation through the driver entry point (no link-time libcuda dep) ----
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                  const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            (void)cudaGetLastError();
+    });
+    return fn;
+}
+
+// bf16 row-major [rows, dim] matrix, box = [64 k-elements x box_rows rows], 128-byte swizzle
+int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t dim, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(DRT_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {dim, rows};
+    cuuint64_t gstride[1] = {dim * 2};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DRT_E_CUDA, "cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
+    return DRT_OK;
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return DRT_OK;
+        if (p) { cudaFree(p); p = nullptr; bytes = 0; }
+        size_t want = need + need / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            e = cudaMalloc(&p, need);
+            want = need;
+        }
+        if (e != cudaSuccess) {
+            (void)cudaGetLastError();
+            p = nullptr;
+            return fail(DRT_E_OOM, "cudaMalloc of %zu bytes failed: %s", need, cudaGetErrorString(e));
+        }
+        bytes = want;
+        return DRT_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; bytes = 0; }
+};
+
+int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+
+}  // namespace
+
+// =============================================================================================
+struct drt_store {
+    int dim = 0;
+    int device = 0;
+    int64_t seg_rows = 0;
+    int64_t ntotal = 0;
+    int sm_count = 148;
+    std::vector<float*> seg_f32;
+    std::vector<void*> seg_bf16;
+    // search workspace (grow-only)
+    DevBuf q_bf16, q_f32, thr, cnt, cand, seg_table, out_scores, out_ids, misc;
+    int* err_host = nullptr;     // pinned + mapped: kernel watchdog code
+    int* err_dev = nullptr;
+    int64_t* misc_host = nullptr;  // pinned: [0] overflow flag [1] flagged count
+    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    bool attrs_set = false;
+};
+
+namespace {
+
+int kprime_for(int k) {
+    int margin = std::max(28, k / 8);
+    return (k + margin + 3) & ~3;
+}
+
+int set_kernel_attrs(drt_store* s) {
+    if (s->attrs_set) return DRT_OK;
+    CUDA_TRY(cudaFuncSetAttribute(drt::mips_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)drt::FilterCfg<1>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(drt::mips_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)drt::FilterCfg<2>::kSmemBytes));
+    CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    s->attrs_set = true;
+    return DRT_OK;
+}
+
+template <int kCtas>
+int launch_filter(const CUtensorMap& tq, const CUtensorMap& td, const drt::FilterParams& p, int sm_count,
+                  cudaStream_t st) {
+    const int total = p.num_m_tiles * p.n_tile_count;
+    int clusters = std::min(sm_count / kCtas, total);
+    if (clusters < 1) clusters = 1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * kCtas);
+    cfg.blockDim = dim3(drt::kFilterThreads);
+    cfg.dynamicSmemBytes = drt::FilterCfg<kCtas>::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    CUDA_TRY(cudaLaunchKernelEx(&cfg, drt::mips_filter_kernel<kCtas>, tq, td, p));
+    return DRT_OK;
+}
+
+struct Chunk { int seg; int64_t row0, row1; };   // rows relative to the segment
+
+// Corpus chunk schedule.  Admission thresholds are refreshed between chunks, so chunk sizes
+// grow geometrically: once `seen` rows have been scanned the threshold sits at rank ~keep of
+// `seen`, and a chunk of (growth-1)*seen further rows is expected to admit ~(growth-1)*keep
+// candidates per query, which must fit the candidate buffer.  attempt 2 uses fixed chunks of
+// (cap - keep) rows, which cannot overflow whatever the data order.
+std::vector<Chunk> plan_chunks(int64_t ntotal, int64_t seg_rows, int cap, int keep, int attempt) {
+    std::vector<Chunk> out;
+    std::vector<int64_t> bounds;
+    const int64_t first = std::max<int64_t>(256, (cap / 2) / 256 * 256);
+    int64_t growth = std::max<int64_t>(2, std::min<int64_t>(8, 1 + (cap - keep) / (2 * (int64_t)keep)));
+    if (attempt == 1) growth = 2;
+    const int64_t fixed = std::max<int64_t>(256, ((int64_t)(cap - keep)) / 256 * 256);
+    int64_t b = 0;
+    while (b < ntotal) {
+        int64_t nb;
+        if (b == 0) nb = first;
+        else if (attempt >= 2) nb = b + fixed;
+        else nb = b * growth;
+        nb = std::min(nb, ntotal);
+        // split at segment boundaries
+        int64_t a = b;
+        while (a < nb) {
+            const int64_t seg = a / seg_rows;
+            const int64_t e = std::min(nb, (seg + 1) * seg_rows);
+            out.push_back({(int)seg, a - seg * seg_rows, e - seg * seg_rows});
+            a = e;
+        }
+        b = nb;
+    }
+    return out;
+}
+
+// One query batch, all on device.  Returns DRT_OK, an error, or +1 = candidate overflow (retry).
+int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
+                 int64_t id_offset, uint32_t flags, cudaStream_t st, int attempt, int kctas) {
+    const int dim = s->dim;
+    const int keep = kprime_for(k);
+    int cap = next_pow2(std::max(4 * keep, 4096));
+    if (attempt >= 1) cap *= 4;
+    if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
+    if (cap < 2 * keep) return fail(DRT_E_UNSUPPORTED, "k=%d too large for the candidate buffer", k);
+
+    int rc;
+    if ((rc = s->q_bf16.ensure((size_t)nq * dim * 2)) != DRT_OK) return rc;
+    if ((rc = s->thr.ensure((size_t)nq * 4)) != DRT_OK) return rc;
+    if ((rc = s->cnt.ensure((size_t)nq * 4)) != DRT_OK) return rc;
+    if ((rc = s->cand.ensure((size_t)nq * cap * 8)) != DRT_OK) return rc;
+    if ((rc = s->misc.ensure(64)) != DRT_OK) return rc;
+    if ((rc = s->seg_table.ensure(std::max<size_t>(8, s->seg_f32.size() * sizeof(float*)))) != DRT_OK) return rc;
+
+    float* thr = (float*)s->thr.p;
+    uint32_t* cnt = (uint32_t*)s->cnt.p;
+    uint64_t* cand = (uint64_t*)s->cand.p;
+    int* overflow = (int*)s->misc.p;
+    unsigned long long* flagged = (unsigned long long*)((char*)s->misc.p + 8);
+
+    CUDA_TRY(cudaMemsetAsync(s->misc.p, 0, 64, st));
+    CUDA_TRY(cudaMemcpyAsync(s->seg_table.p, s->seg_f32.data(), s->seg_f32.size() * sizeof(float*),
+                             cudaMemcpyHostToDevice, st));
+    {
+        const size_t n4 = (size_t)nq * dim / 4;
+        const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)s->sm_count * 8);
+        drt::f32_to_bf16_kernel<<<blocks, 256, 0, st>>>((const float4*)q_dev, (uint2*)s->q_bf16.p, n4);
+        drt::init_query_state_kernel<<<(int)((nq + 255) / 256), 256, 0, st>>>(thr, cnt, (int)nq);
+        s->stats[0] += 2;
+    }
+    CUtensorMap tmap_q;
+    if ((rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
+
+    const std::vector<Chunk> chunks = plan_chunks(s->ntotal, s->seg_rows, cap, keep, attempt);
+    s->stats[6] = (int64_t)chunks.size();
+    CUtensorMap tmap_d;
+    int tmap_seg = -1;
+    for (const Chunk& c : chunks) {
+        const int64_t seg_valid = std::min<int64_t>(s->seg_rows, s->ntotal - (int64_t)c.seg * s->seg_rows);
+        if (c.seg != tmap_seg) {
+            if ((rc = make_tmap_bf16(&tmap_d, s->seg_bf16[c.seg], (uint64_t)seg_valid, (uint64_t)dim,
+                                     drt::kTileN / kctas)) != DRT_OK) return rc;
+            tmap_seg = c.seg;
+        }
+        drt::FilterParams p;
+        p.num_m_tiles = (int)((nq + drt::kTileM * kctas - 1) / (drt::kTileM * kctas));
+        p.n_tile_begin = (int)(c.row0 / drt::kTileN);
+        p.n_tile_count = (int)((c.row1 + drt::kTileN - 1) / drt::kTileN) - p.n_tile_begin;
+        p.num_k_blocks = dim / drt::kBlockK;
+        p.nq = (int)nq;
+        p.rows_valid = (uint32_t)c.row1;    // rows past this chunk's end are not admitted yet
+        p.row_base = (uint32_t)((int64_t)c.seg * s->seg_rows);
+        p.cap = (uint32_t)cap;
+        p.thr = thr; p.cnt = cnt; p.cand = cand; p.err = s->err_dev;
+        rc = (kctas == 2) ? launch_filter<2>(tmap_q, tmap_d, p, s->sm_count, st)
+                          : launch_filter<1>(tmap_q, tmap_d, p, s->sm_count, st);
+        if (rc != DRT_OK) return rc;
+        drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
+        s->stats[0] += 2;
+        s->stats[1] += 1;
+    }
+    {
+        const size_t smem = (size_t)next_pow2(keep) * 8 + (size_t)dim * 4;
+        drt::rescore_kernel<<<(int)nq, 256, smem, st>>>(cand, cnt, (uint32_t)cap, (uint32_t)keep, q_dev, dim,
+                                                       (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
+                                                       (long long)id_offset, out_s, (long long*)out_i,
+                                                       (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged);
+        s->stats[0] += 1;
+    }
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(s->misc_host, s->misc.p, 16, cudaMemcpyDeviceToHost, st));
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        const int code = s->err_host ? *s->err_host : 0;
+        return fail(code ? DRT_E_INTERNAL : DRT_E_CUDA, "search kernels failed: %s (watchdog code %d)",
+                    cudaGetErrorString(e), code);
+    }
+    s->stats[3] = keep;
+    s->stats[5] = kctas;
+    if ((int)(s->misc_host[0] & 0xffffffff) != 0) return 1;   // overflow -> caller retries
+    s->stats[4] += (int64_t)s->misc_host[1];
+    return DRT_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int drt_abi_version(void) { return DRT_B200_ABI_VERSION; }
+const char* drt_last_error(void) { return g_err.c_str(); }
+
+int drt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { (void)cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int d = 0; d < n; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) == cudaSuccess && major == 10) ++ok;
+    }
+    return ok;
+}
+
+int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows) {
+    if (!out) return fail(DRT_E_INVALID, "out is NULL");
+    *out = nullptr;
+    if (dim <= 0) return fail(DRT_E_INVALID, "dim must be positive, got %d", dim);
+    if (dim % 64 != 0) return fail(DRT_E_UNSUPPORTED, "dim %d is not a multiple of 64 (one 128-byte bf16 swizzle span)", dim);
+    if (seg_rows == 0) seg_rows = 1 << 20;
+    if (seg_rows < 256 || seg_rows % 256 != 0) return fail(DRT_E_INVALID, "seg_rows must be a positive multiple of 256");
+    int rc = check_device(device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(device);
+    if (!g.ok) return fail(DRT_E_CUDA, "cudaSetDevice(%d) failed", device);
+    drt_store* s = new (std::nothrow) drt_store();
+    if (!s) return fail(DRT_E_OOM, "host allocation failed");
+    s->dim = dim; s->device = device; s->seg_rows = seg_rows;
+    cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
+    if (cudaHostAlloc((void**)&s->err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+        cudaHostGetDevicePointer((void**)&s->err_dev, s->err_host, 0) != cudaSuccess ||
+        cudaHostAlloc((void**)&s->misc_host, 64, cudaHostAllocDefault) != cudaSuccess) {
+        (void)cudaGetLastError();
+        delete s;
+        return fail(DRT_E_CUDA, "pinned host allocation failed");
+    }
+    *s->err_host = 0;
+    *out = s;
+    return DRT_OK;
+}
+
+int drt_store_destroy(drt_store* s) {
+    if (!s) return DRT_OK;
+    DeviceGuard g(s->device);
+    for (float* p : s->seg_f32) cudaFree(p);
+    for (void* p : s->seg_bf16) cudaFree(p);
+    s->q_bf16.release(); s->q_f32.release(); s->thr.release(); s->cnt.release(); s->cand.release();
+    s->seg_table.release(); s->out_scores.release(); s->out_ids.release(); s->misc.release();
+    if (s->err_host) cudaFreeHost(s->err_host);
+    if (s->misc_host) cudaFreeHost(s->misc_host);
+    (void)cudaGetLastError();
+    delete s;
+    return DRT_OK;
+}
+
+int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device, void* stream) {
+    if (!s) return fail(DRT_E_INVALID, "store is NULL");
+    if (n < 0 || (n > 0 && !rows)) return fail(DRT_E_INVALID, "bad rows/n");
+    if (n == 0) return DRT_OK;
+    if (s->ntotal + n > 0xFFFFFF00ll) return fail(DRT_E_UNSUPPORTED, "a shard holds at most 2^32-256 rows");
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t row_f32 = (size_t)s->dim * 4, row_bf16 = (size_t)s->dim * 2;
+    int64_t done = 0;
+    while (done < n) {
+        const int64_t seg = s->ntotal / s->seg_rows, off = s->ntotal % s->seg_rows;
+        if ((size_t)seg == s->seg_f32.size()) {
+            float* f = nullptr; void* b = nullptr;
+            cudaError_t e = cudaMalloc((void**)&f, (size_t)s->seg_rows * row_f32);
+            if (e == cudaSuccess) e = cudaMalloc(&b, (size_t)s->seg_rows * row_bf16);
+            if (e != cudaSuccess) {
+                (void)cudaGetLastError();
+                if (f) cudaFree(f);
+                return fail(DRT_E_OOM, "allocating corpus segment %lld (%lld rows x %d) failed: %s", (long long)seg,
+                            (long long)s->seg_rows, s->dim, cudaGetErrorString(e));
+            }
+            s->seg_f32.push_back(f); s->seg_bf16.push_back(b);
+        }
+        const int64_t take = std::min(n - done, s->seg_rows - off);
+        float* dst = s->seg_f32[seg] + (size_t)off * s->dim;
+        CUDA_TRY(cudaMemcpyAsync(dst, rows + (size_t)done * s->dim, (size_t)take * row_f32,
+                                 rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        const size_t n4 = (size_t)take * s->dim / 4;
+        const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)s->sm_count * 16);
+        drt::f32_to_bf16_kernel<<<blocks, 256, 0, st>>>((const float4*)dst,
+            (uint2*)((char*)s->seg_bf16[seg] + (size_t)off * row_bf16), n4);
+        CUDA_TRY(cudaGetLastError());
+        s->ntotal += take;
+        done += take;
+    }
+    if (!rows_on_device) CUDA_TRY(cudaStreamSynchronize(st));
+    return DRT_OK;
+}
+
+int64_t drt_store_ntotal(const drt_store* s) { return s ? s->ntotal : -1; }
+int drt_store_dim(const drt_store* s) { return s ? s->dim : -1; }
+int drt_store_device(const drt_store* s) { return s ? s->device : -1; }
+
+int drt_store_reset(drt_store* s) {
+    if (!s) return fail(DRT_E_INVALID, "store is NULL");
+    s->ntotal = 0;
+    return DRT_OK;
+}
+
+int drt_store_reconstruct(const drt_store* s, int64_t row0, int64_t n, float* out, int out_on_device, void* stream) {
+    if (!s || (n > 0 && !out)) return fail(DRT_E_INVALID, "bad arguments");
+    if (row0 < 0 || n < 0 || row0 + n > s->ntotal) return fail(DRT_E_INVALID, "rows [%lld,%lld) out of range", (long long)row0, (long long)(row0 + n));
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t done = 0;
+    while (done < n) {
+        const int64_t r = row0 + done, seg = r / s->seg_rows, off = r % s->seg_rows;
+        const int64_t take = std::min(n - done, s->seg_rows - off);
+        CUDA_TRY(cudaMemcpyAsync(out + (size_t)done * s->dim, s->seg_f32[seg] + (size_t)off * s->dim,
+                                 (size_t)take * s->dim * 4,
+                                 out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        done += take;
+    }
+    if (!out_on_device) CUDA_TRY(cudaStreamSynchronize(st));
+    return DRT_OK;
+}
+
+int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_scores, int64_t* out_ids,
+               int io_on_device, int64_t id_offset, uint32_t flags, void* stream) {
+    if (!s) return fail(DRT_E_INVALID, "store is NULL");
+    if (nq < 0 || k <= 0) return fail(DRT_E_INVALID, "need nq >= 0 and k > 0 (nq=%lld k=%d)", (long long)nq, k);
+    if (k > DRT_MAX_K) return fail(DRT_E_UNSUPPORTED, "k=%d exceeds DRT_MAX_K=%d", k, DRT_MAX_K);
+    if (nq == 0) return DRT_OK;
+    if (!q || !out_scores || !out_ids) return fail(DRT_E_INVALID, "NULL query/output pointer");
+    int rc = check_device(s->device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(s->device);
+    if ((rc = set_kernel_attrs(s)) != DRT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int i = 0; i < 8; ++i) s->stats[i] = 0;
+
+    int kctas = 1;
+    if (const char* e = getenv("DRT_B200_CTAS")) kctas = (atoi(e) == 2) ? 2 : 1;
+    if (flags & DRT_SEARCH_FORCE_1CTA) kctas = 1;
+    if (flags & DRT_SEARCH_FORCE_2CTA) kctas = 2;
+
+    // Query batches bound the candidate workspace (nq_batch * cap * 8 bytes).
+    const int64_t max_batch = 16384;
+    for (int64_t q0 = 0; q0 < nq; q0 += max_batch) {
+        const int64_t nb = std::min(max_batch, nq - q0);
+        const float* q_dev;
+        float* os_dev;
+        int64_t* oi_dev;
+        if (io_on_device) {
+            q_dev = q + (size_t)q0 * s->dim;
+            os_dev = out_scores + (size_t)q0 * k;
+            oi_dev = out_ids + (size_t)q0 * k;
+        } else {
+            if ((rc = s->q_f32.ensure((size_t)nb * s->dim * 4)) != DRT_OK) return rc;
+            if ((rc = s->out_scores.ensure((size_t)nb * k * 4)) != DRT_OK) return rc;
+            if ((rc = s->out_ids.ensure((size_t)nb * k * 8)) != DRT_OK) return rc;
+            CUDA_TRY(cudaMemcpyAsync(s->q_f32.p, q + (size_t)q0 * s->dim, (size_t)nb * s->dim * 4, cudaMemcpyHostToDevice, st));
+            q_dev = (const float*)s->q_f32.p;
+            os_dev = (float*)s->out_scores.p;
+            oi_dev = (int64_t*)s->out_ids.p;
+        }
+        if (s->ntotal == 0) {
+            drt::fill_outputs_kernel<<<std::max(1, (int)std::min<int64_t>((nb * k + 255) / 256, 4096)), 256, 0, st>>>(
+                os_dev, (long long*)oi_dev, (size_t)nb * k);
+            CUDA_TRY(cudaGetLastError());
+        } else {
+            int attempt = 0;
+            for (;;) {
+                rc = search_batch(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, attempt, kctas);
+                if (rc <= 0) break;
+                s->stats[2] += 1;
+                if (++attempt > 2) return fail(DRT_E_INTERNAL, "candidate buffer overflow persisted after retries");
+            }
+            if (rc != DRT_OK) return rc;
+        }
+        if (!io_on_device) {
+            CUDA_TRY(cudaMemcpyAsync(out_scores + (size_t)q0 * k, os_dev, (size_t)nb * k * 4, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaMemcpyAsync(out_ids + (size_t)q0 * k, oi_dev, (size_t)nb * k * 8, cudaMemcpyDeviceToHost, st));
+            CUDA_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    return DRT_OK;
+}
+
+int drt_search_stats(const drt_store* s, int64_t out[8]) {
+    if (!s || !out) return fail(DRT_E_INVALID, "bad arguments");
+    for (int i = 0; i < 8; ++i) out[i] = s->stats[i];
+    return DRT_OK;
+}
+
+int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t nq, int k_in, int k_out,
+                   float* out_scores, int64_t* out_ids, int device, void* stream) {
+    if (n_lists <= 0 || nq < 0 || k_in <= 0 || k_out <= 0) return fail(DRT_E_INVALID, "bad merge shape");
+    if (nq == 0) return DRT_OK;
+    if (!scores || !ids || !out_scores || !out_ids) return fail(DRT_E_INVALID, "NULL pointer");
+    const int P = next_pow2(n_lists * k_in);
+    if (P > 8192) return fail(DRT_E_UNSUPPORTED, "merge of %d x %d entries exceeds 8192 per query; merge hierarchically", n_lists, k_in);
+    if (k_out > P) return fail(DRT_E_INVALID, "k_out=%d exceeds the %d merged entries", k_out, P);
+    int rc = check_device(device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(device);
+    static std::once_flag once;
+    std::call_once(once, [] {
+        cudaFuncSetAttribute(drt::merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(drt::MergeEnt));
+    });
+    // the attribute is per device: set it again cheaply (idempotent)
+    CUDA_TRY(cudaFuncSetAttribute(drt::merge_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 8192 * (int)sizeof(drt::MergeEnt)));
+    drt::merge_topk_kernel<<<(int)nq, 256, (size_t)P * sizeof(drt::MergeEnt), (cudaStream_t)stream>>>(
+        n_lists, scores, (const long long*)ids, (long long)nq, k_in, k_out, out_scores, (long long*)out_ids);
+    CUDA_TRY(cudaGetLastError());
+    return DRT_OK;
+}
+
+// ---- in-batch CE ----------------------------------------------------------------------------
+namespace {
+struct CeWorkspace { DevBuf part_max, part_sum, tgt, ticket; bool ticket_init = false; };
+std::mutex g_ce_mu;
+std::map<int, CeWorkspace> g_ce_ws;
+}  // namespace
+
+int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int dim, const int64_t* target,
+                       float loss_scale, float* logits_out, float* lse_out, float* loss_rows, float* loss_out,
+                       int device, void* stream) {
+    if (B <= 0 || P <= 0 || dim <= 0) return fail(DRT_E_INVALID, "bad shape B=%lld P=%lld d=%d", (long long)B, (long long)P, dim);
+    if (dim % 32 != 0) return fail(DRT_E_UNSUPPORTED, "dim %d is not a multiple of 32", dim);
+    if (!x || !y || !lse_out || !loss_rows || !loss_out) return fail(DRT_E_INVALID, "NULL pointer");
+    if (!target && P / B == 0) return fail(DRT_E_INVALID, "default targets need P >= B");
+    int rc = check_device(device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    std::lock_guard<std::mutex> lk(g_ce_mu);
+    CeWorkspace& w = g_ce_ws[device];
+    const int ncol = (int)((P + drt::kCeTN - 1) / drt::kCeTN), nrow = (int)((B + drt::kCeTM - 1) / drt::kCeTM);
+    if ((rc = w.part_max.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
+    if ((rc = w.part_sum.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
+    if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
+    if ((rc = w.ticket.ensure(64)) != DRT_OK) return rc;
+    if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, 64, st)); w.ticket_init = true; }
+    CUDA_TRY(cudaMemsetAsync(w.tgt.p, 0xFF, (size_t)B * 4, st));   // NaN: an out-of-range target poisons the loss
+    drt::inbatch_ce_fwd_kernel<<<dim3(ncol, nrow), drt::kCeThreads, 0, st>>>(
+        x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), loss_scale, logits_out,
+        (float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows, loss_out);
+    CUDA_TRY(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim, const int64_t* target,
+                       const float* lse, const float* grad_rows, float* work, float* dx, float* dy, int device,
+                       void* stream) {
+    if (B <= 0 || P <= 0 || dim <= 0) return fail(DRT_E_INVALID, "bad shape");
+    if (dim % 32 != 0) return fail(DRT_E_UNSUPPORTED, "dim %d is not a multiple of 32", dim);
+    if (!x || !y || !lse || !grad_rows || !work) return fail(DRT_E_INVALID, "NULL pointer");
+    int rc = check_device(device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int ncol = (int)((P + drt::kCeTN - 1) / drt::kCeTN), nrow = (int)((B + drt::kCeTM - 1) / drt::kCeTM);
+    drt::inbatch_ce_dlogits_kernel<<<dim3(ncol, nrow), drt::kCeThreads, 0, st>>>(
+        x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), lse, grad_rows, work);
+    if (dx) drt::sgemm_strided_kernel<<<dim3((dim + 63) / 64, (unsigned)((B + 63) / 64)), 256, 0, st>>>(
+        work, (long long)P, 1ll, y, (long long)B, (long long)dim, (long long)P, dx);
+    if (dy) drt::sgemm_strided_kernel<<<dim3((dim + 63) / 64, (unsigned)((P + 63) / 64)), 256, 0, st>>>(
+        work, 1ll, (long long)P, x, (long long)P, (long long)dim, (long long)B, dy);
+    CUDA_TRY(cudaGetLastError());
+    return DRT_OK;
+}
+
+int drt_filter_negatives(const int64_t* ids, int64_t nq, int k, const int64_t* pos_begin, const int64_t* pos_end,
+                         int num_negative, int64_t* out_ids, int device, void* stream) {
+    if (nq < 0 || k <= 0 || num_negative <= 0) return fail(DRT_E_INVALID, "bad shape");
+    if (nq == 0) return DRT_OK;
+    if (!ids || !pos_begin || !pos_end || !out_ids) return fail(DRT_E_INVALID, "NULL pointer");
+    int rc = check_device(device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(device);
+    const int64_t threads = nq * 32;
+    drt::filter_negatives_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        (const long long*)ids, (long long)nq, k, (const long long*)pos_begin, (const long long*)pos_end, num_negative,
+        (long long*)out_ids);
+    CUDA_TRY(cudaGetLastError());
+    return DRT_OK;
+}
+
+}  // extern "C"

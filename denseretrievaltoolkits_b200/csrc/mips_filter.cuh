@@ -1,0 +1,285 @@
+// mips_filter.cuh — K1: bf16 Q·Dᵀ on tcgen05 with a fused per-query threshold filter.
+//
+// Replaces the arithmetic of faiss.IndexFlatIP.search as called from
+// DRT/evaluator/index.py:32 (sgemm blocks + heap k-selection on the CPU).
+//
+// Shape of the problem: scores[q, r] = <query q, corpus row r>, q in [0,nq), r in one corpus
+// segment.  The kernel never writes the score matrix.  Queries sit on the MMA M dimension, so an
+// accumulator row (= one TMEM lane) belongs to one query and ONE epilogue thread owns it: that
+// thread keeps the query's current admission threshold in a register, streams the 256 scores of
+// its lane out of TMEM with tcgen05.ld, and only when a score beats the threshold appends
+// (score,row) to the query's candidate list in global memory (rare: O(k log N) per query).
+//
+// Roles inside a CTA (192 threads):
+//   warp 0    TMA producer: streams 128x64 query k-blocks and 256x64 (128x64 per CTA in pair
+//             mode) corpus k-blocks into a 128B-swizzled smem ring.
+//   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128*kCtas, N=256, K=16) four times per
+//             k-block into one of two 256-column TMEM accumulator stages; tcgen05.commit frees
+//             smem slots and publishes finished accumulators.
+//   warps 2-5 epilogue: one warp per TMEM lane quarter; overlaps with the MMA of the next tile
+//             through the second accumulator stage.
+// kCtas = 2 runs the same protocol on a CTA pair (cta_group::2): each CTA owns 128 queries and
+// loads half of every corpus tile, halving L2->SM operand traffic per FLOP.
+//
+// Tiles are walked persistently, query-tile fastest, so the CTAs resident at any moment share
+// the same few corpus tiles (one HBM read, L2 hits for the rest) while the whole bf16 query
+// matrix stays L2 resident.
+#pragma once
+#include "ptx.cuh"
+
+namespace drt {
+
+constexpr int kTileM = 128;     // queries per CTA
+constexpr int kTileN = 256;     // corpus rows per tile (per CTA pair in pair mode)
+constexpr int kBlockK = 64;     // bf16 elements per k-block = one 128-byte swizzle span
+constexpr int kFilterThreads = 192;
+
+struct FilterParams {
+    int num_m_tiles;        // ceil(nq / (128 * kCtas))
+    int n_tile_begin;       // first 256-row tile of this launch, relative to the segment
+    int n_tile_count;
+    int num_k_blocks;       // dim / 64
+    int nq;
+    uint32_t rows_valid;    // rows present in this segment
+    uint32_t row_base;      // store row id of the segment's first row
+    uint32_t cap;           // candidate slots per query
+    const float* thr;       // [nq] admission threshold (strict >)
+    uint32_t* cnt;          // [nq] candidates appended so far (may exceed cap: overflow)
+    uint64_t* cand;         // [nq][cap] packed (ordered score << 32 | ~row)
+    int* err;               // host-mapped watchdog flag
+};
+
+// Monotone map float -> uint32 (ascending), so packed keys sort like (score, then lower row id
+// first when sorted descending).
+__device__ __forceinline__ uint32_t float_to_ordered(float f) {
+    uint32_t b = __float_as_uint(f);
+    return b ^ ((b & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float ordered_to_float(uint32_t o) {
+    uint32_t b = o ^ ((o & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu);
+    return __uint_as_float(b);
+}
+__device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
+    return (static_cast<uint64_t>(float_to_ordered(score)) << 32) | (0xFFFFFFFFu - row);
+}
+
+template <int kCtas>
+struct FilterCfg {
+    static constexpr int kStages = (kCtas == 1) ? 4 : 6;
+    static constexpr uint32_t kABytes = kTileM * kBlockK * 2;             // 16 KB
+    static constexpr uint32_t kBRows = kTileN / kCtas;                    // rows this CTA loads
+    static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;             // 32 KB | 16 KB
+    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+};
+
+// wait for all outstanding tcgen05.ld; the register operands tie later uses to this point
+__device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]),
+                   "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]),
+                   "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]),
+                   "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
+
+// Filter 32 consecutive scores of one query (registers v) against thr.
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr, uint32_t row0,
+                                             const FilterParams& p, int q) {
+    float m = __uint_as_float(v[0]);
+#pragma unroll
+    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
+    if (m > thr) {  // rare once the threshold has warmed up
+        uint32_t hit = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const bool h = (__uint_as_float(v[j]) > thr) && (row0 + j < p.rows_valid);
+            hit |= (h ? 1u : 0u) << j;
+        }
+        if (hit) {
+            uint32_t slot = atomicAdd(p.cnt + q, __popc(hit));
+            uint64_t* dst = p.cand + static_cast<size_t>(q) * p.cap;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                if (hit & (1u << j)) {
+                    if (slot < p.cap)
+                        dst[slot] = pack_key(__uint_as_float(v[j]), p.row_base + row0 + j);
+                    ++slot;
+                }
+            }
+        }
+    }
+    __syncwarp();   // the caller continues with warp-aligned tcgen05 instructions
+}
+
+template <int kCtas>
+__global__ void __launch_bounds__(kFilterThreads, 1)
+mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
+                   const __grid_constant__ CUtensorMap tmap_d, const FilterParams p) {
+    using Cfg = FilterCfg<kCtas>;
+    constexpr int kStages = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t rank = (kCtas == 2) ? ptx::cluster_ctarank() : 0u;
+
+    // ---- shared memory carve-up (shared::cta addresses; tiles 1024-byte aligned) ----
+    const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + kStages * Cfg::kStageBytes;
+    auto smem_a = [&](int s) { return base + s * Cfg::kStageBytes; };
+    auto smem_b = [&](int s) { return base + s * Cfg::kStageBytes + Cfg::kABytes; };
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (kStages + s); };
+    auto tfull_bar = [&](int a) { return bars + 8u * (2 * kStages + a); };
+    auto tempty_bar = [&](int a) { return bars + 8u * (2 * kStages + 2 + a); };
+    const uint32_t tmem_holder = bars + 8u * (2 * kStages + 4);
+
+    if constexpr (kCtas == 2) ptx::cluster_sync_all();
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tmap(&tmap_q);
+        ptx::prefetch_tmap(&tmap_d);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            ptx::mbar_init(full_bar(s), kCtas);   // pair mode: leader + peer producer arrive
+            ptx::mbar_init(empty_bar(s), 1);      // one tcgen05.commit
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(tfull_bar(a), 1);           // one tcgen05.commit
+            ptx::mbar_init(tempty_bar(a), 4 * kCtas);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<kCtas>(tmem_holder, 512);
+    ptx::tc_fence_before();
+    if constexpr (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();
+    ptx::tc_fence_after();
+    uint32_t tmem_base;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_holder));
+
+    const int cluster_id = blockIdx.x / kCtas;
+    const int num_clusters = gridDim.x / kCtas;
+    const int total_tiles = p.num_m_tiles * p.n_tile_count;
+    const int nkb = p.num_k_blocks;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (ptx::elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                const int m_tile = t % p.num_m_tiles;
+                const int n_tile = p.n_tile_begin + t / p.num_m_tiles;
+                const int q_row = (m_tile * kCtas + static_cast<int>(rank)) * kTileM;
+                const int d_row = n_tile * kTileN + static_cast<int>(rank) * Cfg::kBRows;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 101);
+                    if constexpr (kCtas == 1) {
+                        ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                        ptx::tma_load_2d(smem_a(stage), &tmap_q, full_bar(stage), kb * kBlockK,
+                                         q_row, ptx::kEvictLast);
+                        ptx::tma_load_2d(smem_b(stage), &tmap_d, full_bar(stage), kb * kBlockK,
+                                         d_row, ptx::kEvictNormal);
+                    } else {
+                        // both CTAs signal the LEADER's full barrier
+                        const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+                        ptx::tma_load_2d_pair(smem_a(stage), &tmap_q, lead_full, kb * kBlockK,
+                                              q_row, ptx::kEvictLast);
+                        ptx::tma_load_2d_pair(smem_b(stage), &tmap_d, lead_full, kb * kBlockK,
+                                              d_row, ptx::kEvictNormal);
+                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                        else           ptx::mbar_arrive_cluster(lead_full);
+                    }
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ==================================
+        if (rank == 0 && ptx::elect_one()) {
+            const uint32_t idesc = ptx::make_idesc_bf16(kTileM * kCtas, kTileN);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 102);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kTileN;
+                for (int kb = 0; kb < nkb; ++kb) {
+                    ptx::mbar_wait(full_bar(stage), phase, p.err, 103);
+                    ptx::tc_fence_after();
+                    const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a(stage));
+                    const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b(stage));
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // +32 bytes (= 16 bf16) along K inside the swizzle span: +2 in the
+                        // 16-byte-granular start-address field
+                        ptx::umma_bf16<kCtas>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                              (kb | k) != 0 ? 1u : 0u);
+                    }
+                    ptx::umma_commit<kCtas>(empty_bar(stage));      // smem slot free when read
+                    if (kb == nkb - 1) ptx::umma_commit<kCtas>(tfull_bar(acc));  // accumulator done
+                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else {
+        // ================================ epilogue ====================================
+        const uint32_t quarter = warp & 3u;   // TMEM lanes [32*quarter, +32) belong to this warp
+        const uint32_t lead_tempty0 = (kCtas == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+        int it = 0;
+        for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
+            const int m_tile = t % p.num_m_tiles;
+            const int n_tile = p.n_tile_begin + t / p.num_m_tiles;
+            const int acc = it & 1;
+            const uint32_t acc_phase = (it >> 1) & 1u;
+            const int q = (m_tile * kCtas + static_cast<int>(rank)) * kTileM + quarter * 32 + lane;
+            const float thr = (q < p.nq) ? p.thr[q] : __int_as_float(0x7f800000);
+            const int qc = (q < p.nq) ? q : 0;
+
+            ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err, 104);
+            ptx::tc_fence_after();
+
+            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN;
+            const uint32_t row0 = static_cast<uint32_t>(n_tile) * kTileN;
+            uint32_t va[32], vb[32];
+            ptx::tmem_ld_32x32(taddr, va);
+#pragma unroll 1
+            for (int c = 0; c < kTileN / 32; c += 2) {
+                tmem_ld_wait_regs(va);
+                ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                filter_chunk(va, thr, row0 + c * 32, p, qc);
+                tmem_ld_wait_regs(vb);
+                if (c + 2 < kTileN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                filter_chunk(vb, thr, row0 + (c + 1) * 32, p, qc);
+            }
+            // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if constexpr (kCtas == 1) {
+                    ptx::mbar_arrive(tempty_bar(acc));
+                } else {
+                    if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+                    else           ptx::mbar_arrive_cluster(lead_tempty0 + 8u * acc);
+                }
+            }
+        }
+    }
+
+    // ---- teardown ----
+    __syncwarp();
+    ptx::tc_fence_before();
+    if constexpr (kCtas == 2) ptx::cluster_sync_all(); else __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<kCtas>(tmem_base, 512);
+}
+
+}  // namespace drt

@@ -1,0 +1,251 @@
+// select_kernels.cuh — the integer/index side of the search path: candidate-list trimming and
+// threshold publication (between corpus chunks), exact fp32 rescoring + final ordering, the
+// fp32->bf16 ingest conversion, the cross-shard merge and the mining filter.
+//
+// These are HBM/L2-bound byte and index kernels: coalesced loads, shared-memory staging, no
+// tensor cores.
+#pragma once
+#include <cuda_bf16.h>
+#include <cfloat>
+#include "mips_filter.cuh"
+
+namespace drt {
+
+__device__ __forceinline__ int next_pow2_dev(int n) {
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// In-place descending bitonic sort of P (power of two) 64-bit keys in shared memory.
+__device__ __forceinline__ void bitonic_sort_desc_u64(uint64_t* keys, int P) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool desc = (lo & size) == 0;
+                const uint64_t a = keys[lo], b = keys[hi];
+                if ((a < b) == desc) { keys[lo] = b; keys[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void init_query_state_kernel(float* thr, uint32_t* cnt, int nq) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nq) { thr[i] = -FLT_MAX; cnt[i] = 0u; }   // faiss: heap starts at -FLT_MAX
+}
+
+// K-select: one CTA per query.  If the query gathered more than `keep` candidates, sort them,
+// keep the best `keep` (score desc, row asc) and publish the keep-th score as the new admission
+// threshold.  Chunks are visited in ascending row order and admission is strict (>), so a later
+// row that ties the threshold loses to the earlier one — the same outcome as faiss' heap.
+__global__ void __launch_bounds__(256)
+select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t keep,
+              int* overflow) {
+    extern __shared__ uint64_t s_keys[];
+    const int q = blockIdx.x;
+    uint32_t n = cnt[q];
+    if (n > cap) {                       // appends were dropped: the host must redo the search
+        if (threadIdx.x == 0) *overflow = 1;
+        n = cap;
+    }
+    if (n <= keep) return;
+    const int P = next_pow2_dev(static_cast<int>(n));
+    uint64_t* row = cand + static_cast<size_t>(q) * cap;
+    for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = (i < static_cast<int>(n)) ? row[i] : 0ull;
+    bitonic_sort_desc_u64(s_keys, P);
+    for (int i = threadIdx.x; i < static_cast<int>(keep); i += blockDim.x) row[i] = s_keys[i];
+    if (threadIdx.x == 0) {
+        cnt[q] = keep;
+        thr[q] = ordered_to_float(static_cast<uint32_t>(s_keys[keep - 1] >> 32));
+    }
+}
+
+// K2: exact fp32 rescoring of the first-pass candidates + final ordering + output.
+// One CTA per query; each warp computes whole dot products (coalesced float4 row reads).
+// Replaces the fp32 exactness of faiss' sgemm for the rows that can still matter.
+__global__ void __launch_bounds__(256)
+rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t keep,
+               const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
+               int k, long long id_offset, float* out_scores, long long* out_ids,
+               int do_rescore, unsigned long long* flagged) {
+    extern __shared__ uint64_t s_keys[];            // [P] then dim floats
+    const int q = blockIdx.x;
+    const int n = static_cast<int>(min(min(cnt[q], cap), keep));
+    const int P = next_pow2_dev(max(n, 1));
+    float* s_q = reinterpret_cast<float*>(s_keys + next_pow2_dev(static_cast<int>(keep)));
+    __shared__ unsigned int s_emax;   // max |approx - exact| (bits of a non-negative float)
+    __shared__ unsigned int s_amin;   // min approx score (ordered encoding)
+    if (threadIdx.x == 0) { s_emax = 0u; s_amin = 0xFFFFFFFFu; }
+    for (int j = threadIdx.x; j < dim; j += blockDim.x) s_q[j] = q_f32[static_cast<size_t>(q) * dim + j];
+    __syncthreads();
+
+    const uint64_t* row = cand + static_cast<size_t>(q) * cap;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    if (do_rescore) {
+        const float4* q4 = reinterpret_cast<const float4*>(s_q);
+        for (int i = warp; i < n; i += nwarps) {
+            const uint64_t key = row[i];
+            const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(key);
+            const uint32_t seg = r / seg_rows, local = r - seg * seg_rows;
+            const float4* x4 = reinterpret_cast<const float4*>(seg_f32[seg] + static_cast<size_t>(local) * dim);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            for (int j = lane; j < (dim >> 2); j += 32) {
+                const float4 x = __ldg(x4 + j);
+                const float4 y = q4[j];
+                a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
+                a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
+            }
+            float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) {
+                const uint32_t approx_o = static_cast<uint32_t>(key >> 32);
+                const float approx = ordered_to_float(approx_o);
+                const bool ok = acc > -FLT_MAX;    // also false for NaN
+                s_keys[i] = ok ? pack_key(acc, r) : 0ull;
+                atomicMin(&s_amin, approx_o);
+                if (ok) atomicMax(&s_emax, __float_as_uint(fabsf(acc - approx)));
+            }
+        }
+    } else {
+        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = row[i];
+    }
+    for (int i = n + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = 0ull;
+    bitonic_sort_desc_u64(s_keys, P);
+
+    for (int i = threadIdx.x; i < k; i += blockDim.x) {
+        const uint64_t key = (i < P) ? s_keys[i] : 0ull;
+        const size_t o = static_cast<size_t>(q) * k + i;
+        if (key != 0ull) {
+            out_scores[o] = ordered_to_float(static_cast<uint32_t>(key >> 32));
+            out_ids[o] = id_offset + static_cast<long long>(0xFFFFFFFFu - static_cast<uint32_t>(key));
+        } else {
+            out_scores[o] = -FLT_MAX;
+            out_ids[o] = -1;
+        }
+    }
+    // Exactness check: rows that never became candidates have bf16 score <= a_min.  If the
+    // candidate list was full and a_min plus twice the largest observed bf16 error reaches the
+    // exact k-th score, a non-candidate could belong to the top-k: count the query as flagged.
+    if (threadIdx.x == 0 && do_rescore && n == static_cast<int>(keep) && n >= k && s_keys[k - 1] != 0ull) {
+        const float tau = ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32));
+        const float amin = ordered_to_float(s_amin);
+        const float emax = __uint_as_float(s_emax);
+        if (amin + 2.f * emax >= tau) atomicAdd(flagged, 1ull);
+    }
+}
+
+// K6 ingest: fp32 rows -> bf16 plane (round to nearest even), 16 B in / 8 B out per thread step
+__global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        const float4 v = in[i];
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+        const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+        uint2 o;
+        o.x = *reinterpret_cast<const uint32_t*>(&lo);
+        o.y = *reinterpret_cast<const uint32_t*>(&hi);
+        out[i] = o;
+    }
+}
+
+__global__ void fill_outputs_kernel(float* scores, long long* ids, size_t n) {
+    for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<size_t>(gridDim.x) * blockDim.x) {
+        scores[i] = -FLT_MAX;
+        ids[i] = -1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K3 cross-shard merge (merge_retrieval_results_by_score, DRT/model/utils.py:215-229).
+struct MergeEnt { float s; int src; long long id; };
+
+template <class Less>
+__device__ __forceinline__ void bitonic_sort_ents(MergeEnt* e, int P, Less less) {
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < (P >> 1); i += blockDim.x) {
+                const int lo = 2 * i - (i & (stride - 1));
+                const int hi = lo + stride;
+                const bool fwd = (lo & size) == 0;
+                const MergeEnt a = e[lo], b = e[hi];
+                if (less(b, a) == fwd && (less(b, a) || less(a, b))) { e[lo] = b; e[hi] = a; }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(256)
+merge_topk_kernel(int G, const float* scores, const long long* ids, long long nq, int k_in,
+                  int k_out, float* out_scores, long long* out_ids) {
+    extern __shared__ uint64_t s_raw[];
+    MergeEnt* e = reinterpret_cast<MergeEnt*>(s_raw);
+    const long long q = blockIdx.x;
+    const int n = G * k_in;
+    const int P = next_pow2_dev(n);
+    for (int i = threadIdx.x; i < P; i += blockDim.x) {
+        MergeEnt m;
+        if (i < n) {
+            const int g = i / k_in, j = i - g * k_in;
+            const size_t o = (static_cast<size_t>(g) * nq + q) * k_in + j;
+            m.s = scores[o]; m.id = ids[o]; m.src = i;
+            if (m.id < 0 || !(m.s > -FLT_MAX)) { m.id = -1; m.s = -FLT_MAX; }
+        } else { m.s = -FLT_MAX; m.id = -1; m.src = i; }
+        e[i] = m;
+    }
+    // pass 1: by (id asc, src asc), padding last -> duplicates of an id become adjacent with the
+    // first partition's copy in front (utils.py:224-226: first partition that mentions it wins)
+    bitonic_sort_ents(e, P, [](const MergeEnt& a, const MergeEnt& b) {
+        const unsigned long long ia = static_cast<unsigned long long>(a.id), ib = static_cast<unsigned long long>(b.id);
+        return ia < ib || (ia == ib && a.src < b.src);   // id -1 -> 0xFFFF... sorts last
+    });
+    bool dup[32];  // P <= 8192, 256 threads -> <= 32 entries per thread
+    int c = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x, ++c) dup[c] = (i > 0 && e[i].id >= 0 && e[i].id == e[i - 1].id);
+    __syncthreads();
+    c = 0;
+    for (int i = threadIdx.x; i < P; i += blockDim.x, ++c) if (dup[c]) { e[i].id = -1; e[i].s = -FLT_MAX; }
+    // pass 2: canonical result order (score desc, id asc), padding last
+    bitonic_sort_ents(e, P, [](const MergeEnt& a, const MergeEnt& b) {
+        if (a.s != b.s) return a.s > b.s;
+        return static_cast<unsigned long long>(a.id) < static_cast<unsigned long long>(b.id);
+    });
+    for (int i = threadIdx.x; i < k_out; i += blockDim.x) {
+        const size_t o = static_cast<size_t>(q) * k_out + i;
+        if (i < P && e[i].id >= 0) { out_scores[o] = e[i].s; out_ids[o] = e[i].id; }
+        else { out_scores[o] = -FLT_MAX; out_ids[o] = -1; }
+    }
+}
+
+// Mining filter (process_sample, DRT/trainer/sampler.py:69-80): one warp per query, ballot
+// compaction keeps rank order.
+__global__ void filter_negatives_kernel(const long long* ids, long long nq, int k,
+                                        const long long* pos_begin, const long long* pos_end,
+                                        int num_negative, long long* out) {
+    const long long q = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (q >= nq) return;
+    const long long b = pos_begin[q], e = pos_end[q];
+    int kept = 0;
+    for (int j0 = 0; j0 < k && kept < num_negative; j0 += 32) {
+        const int j = j0 + lane;
+        const long long d = (j < k) ? ids[q * k + j] : -1;
+        const bool keep = d >= 0 && !(d >= b && d < e);
+        const unsigned m = __ballot_sync(0xffffffffu, keep);
+        const int pos = kept + __popc(m & ((1u << lane) - 1u));
+        if (keep && pos < num_negative) out[q * num_negative + pos] = d;
+        kept += __popc(m);
+    }
+    kept = min(kept, num_negative);
+    for (int j = kept + lane; j < num_negative; j += 32) out[q * num_negative + j] = -1;
+}
+
+}  // namespace drt

@@ -1,0 +1,135 @@
+/*
+ * drt_b200.h — C ABI of the B200-native exact-MIPS hot path for DenseRetrievalToolkits.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes / a CUDA stream handle passed
+ * as `void*` (a `cudaStream_t`; NULL = the legacy default stream), returns an `int` status
+ * (0 = ok, < 0 = DRT_E_*), and never lets a C++ exception cross the boundary.  The thread-local
+ * message of the last failure is returned by drt_last_error().  There is NO CPU fallback: on a
+ * machine without an sm_100 device every compute call fails with DRT_E_NO_DEVICE.
+ *
+ * Each function cites the interface of the reference it stands in for.  Citations are
+ * `path:line` into yhao-wang/DenseRetrievalToolkits (the reference is pure Python; the
+ * arithmetic it delegates to faiss / torch is what these functions replace).
+ */
+#ifndef DRT_B200_H_
+#define DRT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DRT_B200_ABI_VERSION 1
+
+/* status codes */
+#define DRT_OK                0
+#define DRT_E_INVALID        -1   /* bad argument (shape, k, dim, null pointer)            */
+#define DRT_E_CUDA           -2   /* a CUDA runtime / driver call failed                   */
+#define DRT_E_NO_DEVICE      -3   /* no CUDA device, or the device is not sm_100 (B200)     */
+#define DRT_E_OOM            -4   /* device allocation failed                              */
+#define DRT_E_UNSUPPORTED    -5   /* e.g. dim % 64 != 0, k > DRT_MAX_K, non-"Flat" factory  */
+#define DRT_E_INTERNAL       -6   /* kernel-side watchdog / invariant violation             */
+
+#define DRT_MAX_K          2048   /* same ceiling faiss-gpu uses for k-selection            */
+
+/* drt_search flags */
+#define DRT_SEARCH_DEFAULT        0u
+#define DRT_SEARCH_NO_RESCORE     1u  /* debug: return the bf16 first-pass scores/order       */
+#define DRT_SEARCH_FORCE_1CTA     2u  /* use the 1-CTA (M=128) tile variant of the MMA kernel */
+#define DRT_SEARCH_FORCE_2CTA     4u  /* use the CTA-pair (M=256, cta_group::2) variant       */
+
+typedef struct drt_store drt_store;   /* opaque: one device-resident corpus shard */
+
+/* ---- library ------------------------------------------------------------------------------ */
+
+int         drt_abi_version(void);
+const char* drt_last_error(void);
+/* Number of CUDA devices that are sm_100; < 0 on error.  Does not create a context. */
+int         drt_device_count(void);
+
+/* ---- corpus-embedding store (one shard) ----------------------------------------------------
+ * Replaces faiss.IndexFlatIP as used by BaseFaissIPRetriever (DRT/evaluator/index.py:16-28) and
+ * the .npy/.json + faiss.write_index/read_index round trip of Trainer._encoding_corpus /
+ * _index_corpus / _load_index (DRT/trainer/trainer.py:191-262).                               */
+
+/* faiss.IndexFlatIP(d) (index.py:19,23).  `seg_rows` = rows per device segment (0 = default
+ * 1<<20); rows live in fixed-size segments so `add` never reallocates or moves data. */
+int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows);
+int drt_store_destroy(drt_store* s);
+
+/* index.add(x) (index.py:28; trainer.py:235): append n fp32 rows, ids = insertion order.
+ * `rows` is a host pointer (rows_on_device = 0) or a device pointer on the store's device
+ * (rows_on_device = 1, the zero-copy path for encoder outputs, trainer.py:204).
+ * Stream-ordered on `stream`; with a host source the call returns after the copy completed. */
+int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device, void* stream);
+
+int64_t drt_store_ntotal(const drt_store* s);   /* index.ntotal */
+int     drt_store_dim(const drt_store* s);      /* index.d      */
+int     drt_store_device(const drt_store* s);
+int     drt_store_reset(drt_store* s);          /* index.reset(): drop rows, keep segments  */
+
+/* index.reconstruct_n(row0, n): copy fp32 rows back (host or device destination).  Used by
+ * the faiss.write_index replacement (trainer.py:245). */
+int drt_store_reconstruct(const drt_store* s, int64_t row0, int64_t n, float* out,
+                          int out_on_device, void* stream);
+
+/* ---- search --------------------------------------------------------------------------------
+ * index.search(x, k) -> (D float32[nq,k], I int64[nq,k]) (index.py:32): exact inner product of
+ * every (query,row) pair, per-query top-k sorted by (score desc, id asc); when k > ntotal the
+ * tail is filled with score -FLT_MAX and id -1; NaN scores never enter a result.
+ * ids are `id_offset + row` (id_offset = this shard's first global row id).
+ * io_on_device = 0: q / out_* are host pointers, H2D + D2H copies happen inside the call and it
+ *                   returns when the results are in host memory (the drop-in faiss contract);
+ * io_on_device = 1: all three are device pointers; the call is stream-ordered and asynchronous
+ *                   except for a few bounded host syncs between corpus chunks.                 */
+int drt_search(drt_store* s, const float* q, int64_t nq, int k,
+               float* out_scores, int64_t* out_ids,
+               int io_on_device, int64_t id_offset, uint32_t flags, void* stream);
+
+/* Counters of the last drt_search on this store (for tests and bench.py):
+ *  [0] kernel launches  [1] mma-filter launches  [2] candidate-buffer overflow retries
+ *  [3] first-pass candidates per query (k')      [4] queries whose exactness check flagged
+ *  [5] ctas per tile (1|2)                        [6] corpus chunks  [7] reserved           */
+int drt_search_stats(const drt_store* s, int64_t out[8]);
+
+/* ---- cross-shard merge ---------------------------------------------------------------------
+ * merge_retrieval_results_by_score (DRT/model/utils.py:215-229): union of G per-shard result
+ * lists per query (first occurrence of an id wins), sort by score desc (ties: id asc), keep
+ * k_out.  Inputs are device arrays laid out [G][nq][k_in]; entries with id < 0 are padding. */
+int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t nq, int k_in,
+                   int k_out, float* out_scores, int64_t* out_ids, int device, void* stream);
+
+/* ---- in-batch-negative loss ----------------------------------------------------------------
+ * SimpleContrastiveLoss.forward (DRT/trainer/losses.py:11-17) and the loss block of
+ * DRModel.forward (DRT/model/biencoder.py:107-116): logits = x·yᵀ (fp32), cross entropy against
+ * target[i].  All pointers are device pointers; x is [B,d], y is [P,d], row-major fp32.
+ *   target      int64[B] or NULL (NULL => target[i] = i * (P / B), losses.py:12-15)
+ *   logits_out  float[B,P] or NULL (DROutput.scores, biencoder.py:122; NULL = never stored)
+ *   lse_out     float[B]  (saved for backward)
+ *   loss_rows   float[B]  per-row loss (reduction='none')
+ *   loss_out    float[1]  sum_i loss_rows[i] * loss_scale  (mean: loss_scale = 1/B)          */
+int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int dim,
+                       const int64_t* target, float loss_scale,
+                       float* logits_out, float* lse_out, float* loss_rows, float* loss_out,
+                       int device, void* stream);
+
+/* Backward of the above: dlogits[i,j] = g_i * (softmax(logits)[i,j] - [j == target[i]]), with
+ * g_i = grad_rows[i] (device float[B]); dx = dlogits·y, dy = dlogitsᵀ·x.  `work` is a device
+ * scratch of B*P floats (holds dlogits). dx / dy may be NULL to skip that gradient. */
+int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim,
+                       const int64_t* target, const float* lse, const float* grad_rows,
+                       float* work, float* dx, float* dy, int device, void* stream);
+
+/* ---- mining filter -------------------------------------------------------------------------
+ * process_sample (DRT/trainer/sampler.py:69-80): walk each query's retrieved ids in rank order,
+ * skip ids inside the query's own positive range [pos_begin[i], pos_end[i]), keep the first
+ * `num_negative`; unfilled slots get -1.  Device pointers. */
+int drt_filter_negatives(const int64_t* ids, int64_t nq, int k, const int64_t* pos_begin,
+                         const int64_t* pos_end, int num_negative, int64_t* out_ids,
+                         int device, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DRT_B200_H_ */
