@@ -32,6 +32,7 @@ SEARCH_DEFAULT = 0
 SEARCH_NO_RESCORE = 1
 SEARCH_FORCE_1CTA = 2
 SEARCH_FORCE_2CTA = 4
+SEARCH_TIME_KERNELS = 8
 MAX_K = 2048
 
 _lib = None

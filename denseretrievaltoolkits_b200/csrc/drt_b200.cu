@@ -149,6 +149,7 @@ struct drt_store {
     int64_t* misc_host = nullptr;  // pinned: [0] overflow flag [1] flagged count
     int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     bool attrs_set = false;
+    std::vector<cudaEvent_t> ev;   // per-launch timing events (DRT_SEARCH_TIME_KERNELS)
 };
 
 namespace {
@@ -267,6 +268,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     s->stats[6] = (int64_t)chunks.size();
     CUtensorMap tmap_d;
     int tmap_seg = -1;
+    size_t n_timed = 0;
     for (const Chunk& c : chunks) {
         const int64_t seg_valid = std::min<int64_t>(s->seg_rows, s->ntotal - (int64_t)c.seg * s->seg_rows);
         if (c.seg != tmap_seg) {
@@ -284,9 +286,19 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         p.row_base = (uint32_t)((int64_t)c.seg * s->seg_rows);
         p.cap = (uint32_t)cap;
         p.thr = thr; p.cnt = cnt; p.cand = cand; p.err = s->err_dev;
+        const bool timed = (flags & DRT_SEARCH_TIME_KERNELS) != 0;
+        if (timed) {
+            while (s->ev.size() < 2 * (n_timed + 1)) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                s->ev.push_back(e);
+            }
+            CUDA_TRY(cudaEventRecord(s->ev[2 * n_timed], st));
+        }
         rc = (kctas == 2) ? launch_filter<2>(tmap_q, tmap_d, p, s->sm_count, st)
                           : launch_filter<1>(tmap_q, tmap_d, p, s->sm_count, st);
         if (rc != DRT_OK) return rc;
+        if (timed) { CUDA_TRY(cudaEventRecord(s->ev[2 * n_timed + 1], st)); ++n_timed; }
         drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
         s->stats[0] += 2;
         s->stats[1] += 1;
@@ -310,6 +322,10 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     }
     s->stats[3] = keep;
     s->stats[5] = kctas;
+    for (size_t i = 0; i < n_timed; ++i) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]) == cudaSuccess) s->stats[7] += (int64_t)(ms * 1e6);
+    }
     if ((int)(s->misc_host[0] & 0xffffffff) != 0) return 1;   // overflow -> caller retries
     s->stats[4] += (int64_t)s->misc_host[1];
     return DRT_OK;
@@ -364,6 +380,7 @@ int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows) {
 int drt_store_destroy(drt_store* s) {
     if (!s) return DRT_OK;
     DeviceGuard g(s->device);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     for (float* p : s->seg_f32) cudaFree(p);
     for (void* p : s->seg_bf16) cudaFree(p);
     s->q_bf16.release(); s->q_f32.release(); s->thr.release(); s->cnt.release(); s->cand.release();

@@ -134,7 +134,7 @@ class IndexFlatIP:
         buf = (ctypes.c_int64 * 8)()
         _lib.check(self._lib.drt_search_stats(self._h, buf), "search_stats")
         names = ["launches", "filter_launches", "overflow_retries", "kprime", "flagged_queries",
-                 "ctas_per_tile", "chunks", "reserved"]
+                 "ctas_per_tile", "chunks", "filter_ns"]
         return dict(zip(names, [int(v) for v in buf]))
 
     # ---- reconstruct ------------------------------------------------------------------------

@@ -38,6 +38,7 @@ extern "C" {
 #define DRT_SEARCH_NO_RESCORE     1u  /* debug: return the bf16 first-pass scores/order       */
 #define DRT_SEARCH_FORCE_1CTA     2u  /* use the 1-CTA (M=128) tile variant of the MMA kernel */
 #define DRT_SEARCH_FORCE_2CTA     4u  /* use the CTA-pair (M=256, cta_group::2) variant       */
+#define DRT_SEARCH_TIME_KERNELS    8u  /* bracket every MMA-filter launch with CUDA events     */
 
 typedef struct drt_store drt_store;   /* opaque: one device-resident corpus shard */
 
@@ -90,7 +91,8 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k,
 /* Counters of the last drt_search on this store (for tests and bench.py):
  *  [0] kernel launches  [1] mma-filter launches  [2] candidate-buffer overflow retries
  *  [3] first-pass candidates per query (k')      [4] queries whose exactness check flagged
- *  [5] ctas per tile (1|2)                        [6] corpus chunks  [7] reserved           */
+ *  [5] ctas per tile (1|2)                        [6] corpus chunks
+ *  [7] summed device time of the MMA-filter launches in ns (DRT_SEARCH_TIME_KERNELS only)   */
 int drt_search_stats(const drt_store* s, int64_t out[8]);
 
 /* ---- cross-shard merge ---------------------------------------------------------------------
