@@ -521,6 +521,31 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
     return DRT_OK;
 }
 
+int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_t* out, int max_chunks) {
+    if (ntotal < 0 || seg_rows < 256 || seg_rows % 256 != 0 || k <= 0 || k > DRT_MAX_K || attempt < 0)
+        return fail(DRT_E_INVALID, "bad plan arguments");
+    const int keep = kprime_for(k);
+    int cap = next_pow2(std::max(4 * keep, 4096));
+    if (attempt >= 1) cap *= 4;
+    if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
+    const std::vector<Chunk> chunks = plan_chunks(ntotal, seg_rows, cap, keep, attempt);
+    for (size_t i = 0; i < chunks.size() && (int)i < max_chunks && out; ++i) {
+        out[3 * i] = chunks[i].seg; out[3 * i + 1] = chunks[i].row0; out[3 * i + 2] = chunks[i].row1;
+    }
+    return (int)chunks.size();
+}
+
+int drt_plan_params(int k, int attempt, int* kprime, int* cap_out) {
+    if (k <= 0 || k > DRT_MAX_K) return fail(DRT_E_INVALID, "bad k");
+    const int keep = kprime_for(k);
+    int cap = next_pow2(std::max(4 * keep, 4096));
+    if (attempt >= 1) cap *= 4;
+    if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
+    if (kprime) *kprime = keep;
+    if (cap_out) *cap_out = cap;
+    return DRT_OK;
+}
+
 int drt_search_stats(const drt_store* s, int64_t out[8]) {
     if (!s || !out) return fail(DRT_E_INVALID, "bad arguments");
     for (int i = 0; i < 8; ++i) out[i] = s->stats[i];

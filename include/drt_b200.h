@@ -95,6 +95,13 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k,
  *  [7] summed device time of the MMA-filter launches in ns (DRT_SEARCH_TIME_KERNELS only)   */
 int drt_search_stats(const drt_store* s, int64_t out[8]);
 
+/* Host-side planning, exposed for tests (no device needed).  drt_plan_params: k' (first-pass
+ * candidates kept per query) and the candidate-buffer capacity for retry level `attempt`.
+ * drt_plan_chunks: the corpus chunk schedule of one search as triples (segment, row0, row1)
+ * relative to the segment, written to out[3*i..]; returns the number of chunks (or < 0). */
+int drt_plan_params(int k, int attempt, int* kprime, int* cap);
+int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_t* out, int max_chunks);
+
 /* ---- cross-shard merge ---------------------------------------------------------------------
  * merge_retrieval_results_by_score (DRT/model/utils.py:215-229): union of G per-shard result
  * lists per query (first occurrence of an id wins), sort by score desc (ties: id asc), keep

@@ -1,0 +1,279 @@
+"""GPU (B200) parity tests of the search path, all through the C ABI (ctypes -> libdrt_b200.so).
+
+Bar (BASELINE.json north_star): scores within 1e-4 relative of the reference arithmetic, top-k
+id lists identical except where scores tie within that tolerance, recall@k >= 0.999.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import flat_ip  # noqa: E402
+
+RTOL = 1e-4          # north_star: "scores within 1e-4 relative"
+
+
+def _mk(device=0, d=768, seg_rows=0):
+    from denseretrievaltoolkits_b200 import faiss_compat
+
+    return faiss_compat.IndexFlatIP(d, device=device, seg_rows=seg_rows)
+
+
+def _check_parity(D, I, Dr, Ir, k, n, scale):
+    """ids identical except among scores that tie within tolerance; scores within RTOL."""
+    kk = min(k, n)
+    recall = np.mean([len(set(a[:kk]) & set(b[:kk])) / kk for a, b in zip(I, Ir)])
+    assert recall >= 0.999, recall
+    valid = Ir >= 0
+    np.testing.assert_array_equal(I >= 0, valid)
+    atol = RTOL * scale
+    np.testing.assert_allclose(D[valid], Dr[valid], rtol=RTOL, atol=atol)
+    diff = (I != Ir) & valid
+    # a differing id must sit in a near-tie: the oracle's score at that rank equals ours within tol
+    assert np.all(np.abs(D[diff] - Dr[diff]) <= RTOL * np.abs(Dr[diff]) + atol)
+    assert (np.diff(D, axis=1) <= 0).all()
+    assert ((I[:, kk:] == -1).all() and (D[:, kk:] == np.float32(-3.4028234663852886e38)).all())
+    return recall
+
+
+@pytest.mark.parametrize("ctas", [1, 2])
+@pytest.mark.parametrize("nq,n,k,seg_rows", [(7, 1000, 10, 256), (128, 100000, 100, 1 << 15), (33, 5000, 1000, 2048),
+                                             (3, 5, 8, 256), (65, 777, 50, 256), (300, 40001, 200, 8192)])
+def test_search_matches_oracle(ctas, nq, n, k, seg_rows):
+    from denseretrievaltoolkits_b200 import _lib
+
+    rng = np.random.default_rng(nq * 1000 + n)
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    index = _mk(seg_rows=seg_rows)
+    for part in np.array_split(x, 3):          # several add() calls, ids = insertion order
+        index.add(part)
+    assert index.ntotal == n
+    flags = _lib.SEARCH_FORCE_2CTA if ctas == 2 else _lib.SEARCH_FORCE_1CTA
+    D, I = index.search(q, k, flags=flags)
+    assert D.dtype == np.float32 and I.dtype == np.int64 and D.shape == (nq, k)
+    Dr, Ir = flat_ip.flat_ip_search(x, q, k)
+    _check_parity(D, I, Dr, Ir, k, n, scale=np.sqrt(768.0))
+    st = index.search_stats()
+    assert st["ctas_per_tile"] == ctas and st["filter_launches"] >= 1 and st["overflow_retries"] == 0
+
+
+@pytest.mark.parametrize("name", ["basic", "k_gt_n", "ties", "zeros", "nonfinite"])
+def test_search_matches_reference_wrapper_goldens(golden_dir, name):
+    """The mirror of BaseFaissIPRetriever returns the ids the reference wrapper returned."""
+    from denseretrievaltoolkits_b200.index import BaseFaissIPRetriever
+
+    g = np.load(os.path.join(golden_dir, f"search_{name}.npz"))
+    x, q, k = g["x"], g["q"], int(g["k"])
+    r = BaseFaissIPRetriever(x)
+    assert r.index.ntotal == 0                   # ctor does not add (index.py:18-19)
+    r.add(x)
+    ids = r.search(q, k)
+    D, I = r.search_with_scores(q, k)
+    assert ids.dtype == np.int64 and ids.shape == (q.shape[0], k)
+    np.testing.assert_array_equal(ids, I)
+    if name == "nonfinite":
+        # +inf scores first, NaN / -inf rows never returned; bf16 first pass keeps the finite order
+        assert (I[:, 0] == 6).all() and 5 not in I and 7 not in I
+        fin = np.isfinite(g["D"])
+        same = (I == g["I"]) & fin
+        assert same[fin].mean() > 0.95
+        np.testing.assert_allclose(D[same], g["D"][same], rtol=RTOL, atol=1e-4)
+        return
+    _check_parity(D, I, g["D"], g["I"], k, x.shape[0], scale=np.sqrt(64.0))
+    if name in ("ties", "k_gt_n", "zeros"):
+        np.testing.assert_array_equal(ids, g["wrapper_ids"])     # exact ties: (score desc, id asc)
+    assert r.batch_search(q, k, 2, quiet=True).shape == ids.shape
+
+
+def test_duplicate_rows_tie_break_by_id():
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal((30000, 768), dtype=np.float32)
+    x[-300:] = x[:300]                            # DistributedSampler-style duplicated rows
+    q = rng.standard_normal((64, 768), dtype=np.float32)
+    index = _mk(seg_rows=4096)
+    index.add(x)
+    D, I = index.search(q, 100)
+    Dr, Ir = flat_ip.flat_ip_search(x, q, 100)
+    _check_parity(D, I, Dr, Ir, 100, 30000, scale=np.sqrt(768.0))
+    for r in range(64):                           # equal scores => ascending ids
+        eq = D[r, 1:] == D[r, :-1]
+        assert (I[r, 1:][eq] > I[r, :-1][eq]).all()
+
+
+def test_device_tensor_api_equals_host_api():
+    rng = np.random.default_rng(6)
+    x = rng.standard_normal((20000, 768), dtype=np.float32)
+    q = rng.standard_normal((50, 768), dtype=np.float32)
+    a, b = _mk(seg_rows=4096), _mk(seg_rows=8192)
+    a.add(x)
+    b.add(torch.from_numpy(x).cuda())            # zero-copy ingest of device rows
+    Da, Ia = a.search(q, 64)
+    Db, Ib = b.search(torch.from_numpy(q).cuda(), 64)
+    assert Db.is_cuda and Ib.dtype == torch.int64
+    np.testing.assert_array_equal(Ia, Ib.cpu().numpy())
+    np.testing.assert_array_equal(Da, Db.cpu().numpy())
+    np.testing.assert_array_equal(a.reconstruct_n(100, 50), x[100:150])
+    # idempotence: same call, same bits
+    Da2, Ia2 = a.search(q, 64)
+    np.testing.assert_array_equal(Ia, Ia2)
+    np.testing.assert_array_equal(Da, Da2)
+
+
+def test_adversarial_row_order_triggers_retry_and_stays_exact():
+    """Scores increase with the row id, so every row beats the running threshold: the candidate
+    buffer overflows, the search is redone with safer chunking, results stay exact."""
+    n = 60000
+    rng = np.random.default_rng(7)
+    u = rng.standard_normal(768).astype(np.float32)
+    u /= np.linalg.norm(u)
+    x = (np.linspace(0.0, 40.0, n, dtype=np.float32)[:, None] * u[None, :]
+         + 0.01 * rng.standard_normal((n, 768), dtype=np.float32)).astype(np.float32)
+    q = (u[None, :] * np.linspace(1.0, 2.0, 9, dtype=np.float32)[:, None]).astype(np.float32)
+    index = _mk(seg_rows=1 << 15)
+    index.add(x)
+    D, I = index.search(q, 100)
+    assert index.search_stats()["overflow_retries"] >= 1
+    Dr, Ir = flat_ip.flat_ip_search(x, q, 100)
+    _check_parity(D, I, Dr, Ir, 100, n, scale=40.0)
+
+
+def test_empty_index_and_errors():
+    index = _mk()
+    D, I = index.search(np.zeros((3, 768), np.float32), 5)
+    assert (I == -1).all() and (D == np.float32(-3.4028234663852886e38)).all()
+    with pytest.raises(RuntimeError):
+        index.search(np.zeros((3, 100), np.float32), 5)
+    with pytest.raises(RuntimeError):
+        index.search(np.zeros((3, 768), np.float32), 5000)       # k > DRT_MAX_K
+    from denseretrievaltoolkits_b200 import faiss_compat
+
+    with pytest.raises(RuntimeError):
+        faiss_compat.index_factory(768, "IVF100,PQ8")             # approximate: refused, no fallback
+    assert isinstance(faiss_compat.index_factory(768, "Flat"), faiss_compat.IndexFlatIP)
+
+
+def test_write_read_index_roundtrip(tmp_path):
+    from denseretrievaltoolkits_b200 import faiss_compat
+
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((3000, 128), dtype=np.float32)
+    q = rng.standard_normal((11, 128), dtype=np.float32)
+    a = _mk(d=128, seg_rows=1024)
+    a.add(x)
+    faiss_compat.write_index(a, str(tmp_path / "idx"))
+    b = faiss_compat.read_index(str(tmp_path / "idx"))
+    assert b.ntotal == 3000 and b.d == 128
+    Da, Ia = a.search(q, 30)
+    Db, Ib = b.search(q, 30)
+    np.testing.assert_array_equal(Ia, Ib)
+    np.testing.assert_array_equal(Da, Db)
+
+
+def test_reference_index_module_runs_unmodified_on_faiss_shim(golden_dir):
+    """sys.modules['faiss'] = faiss_compat: code written against faiss (the reference's
+    index.py does `faiss.IndexFlatIP(d)`, `.add`, `.search`) works as is."""
+    import sys
+
+    import denseretrievaltoolkits_b200 as pkg
+
+    saved = sys.modules.get("faiss")
+    try:
+        pkg.install_as_faiss()
+        import faiss
+
+        g = np.load(os.path.join(golden_dir, "search_basic.npz"))
+        idx = faiss.IndexFlatIP(g["x"].shape[1])
+        idx.add(g["x"])
+        scores, indices = idx.search(g["q"], int(g["k"]))
+        ids = np.array([ind[o] for ind, o in zip(indices, np.argsort(-scores))])   # index.py:33
+        np.testing.assert_array_equal(ids, g["wrapper_ids"])
+    finally:
+        if saved is not None:
+            sys.modules["faiss"] = saved
+        else:
+            sys.modules.pop("faiss", None)
+
+
+def test_retrieval_cli_on_gpu(tmp_path):
+    import pickle
+
+    from denseretrievaltoolkits_b200 import retrieval
+
+    rng = np.random.default_rng(9)
+    x = rng.standard_normal((5000, 768), dtype=np.float32)
+    q = rng.standard_normal((20, 768), dtype=np.float32)
+    lookups = []
+    for i, part in enumerate(np.array_split(x, 4)):
+        lk = [f"d{i}_{j}" for j in range(part.shape[0])]
+        lookups += lk
+        pickle.dump((part, lk), open(tmp_path / f"c{i}.pkl", "wb"))
+    pickle.dump((q, list(range(20))), open(tmp_path / "q.pkl", "wb"))
+    scores, psg = retrieval.main(["--query_reps", str(tmp_path / "q.pkl"), "--passage_reps", str(tmp_path / "c*.pkl"),
+                                  "--depth", "100", "--batch_size", "8", "--save_ranking_to", str(tmp_path / "r.tsv"),
+                                  "--save_text", "--quiet"])
+    Dr, Ir = flat_ip.flat_ip_search(x, q, 100)
+    want = np.array([[lookups[i] for i in row] for row in Ir], dtype=object)
+    assert (psg == want).mean() > 0.999
+    assert sum(1 for _ in open(tmp_path / "r.tsv")) == 2000
+
+
+def test_virtual_shards_equal_single_store():
+    """G-shard search + merge kernel == 1-shard search, ids bit for bit."""
+    from denseretrievaltoolkits_b200.store import ShardedCorpusStore
+
+    rng = np.random.default_rng(10)
+    x = rng.standard_normal((50000, 768), dtype=np.float32)
+    x[45000:45100] = x[100:200]                   # ties across shards
+    q = rng.standard_normal((100, 768), dtype=np.float32)
+    single = _mk(seg_rows=8192)
+    single.add(x)
+    Ds, Is = single.search(q, 100)
+    for G in (2, 4, 8):
+        st = ShardedCorpusStore(768, num_virtual_shards=G, device=0, seg_rows=4096)
+        st.add_split(x)
+        assert st.ntotal == 50000
+        D, I = st.search(q, 100)
+        np.testing.assert_array_equal(I, Is)
+        np.testing.assert_array_equal(D, Ds)
+
+
+@pytest.mark.parametrize("k", [100, 1000])
+def test_scale_properties_2m_rows(k):
+    """Size-independent properties at a multi-segment scale (2.1M x 768): agreement with an
+    independent GPU fp32 reference (torch.matmul, TF32 off, + topk) on a query subset,
+    sortedness, score == exact dot of the returned row, idempotence."""
+    import bench
+
+    torch.backends.cuda.matmul.allow_tf32 = False
+    dev = torch.device("cuda", 0)
+    n = 2 * (1 << 20) + 12345
+    index = _mk()
+    bench.fill_rows(torch, index.add, 0, n, dev)
+    nq = 512
+    q = bench.make_queries(torch, nq, dev)
+    D, I = index.search(q, k)
+    assert index.search_stats()["overflow_retries"] == 0
+    assert (D[:, 1:] <= D[:, :-1]).all() and (I >= 0).all() and (I < n).all()
+    sub = slice(0, 64)
+    best_d = torch.full((64, 0), 0.0, device=dev)
+    best_i = torch.zeros((64, 0), dtype=torch.int64, device=dev)
+    for c in range(0, n, bench.CHUNK):
+        rows = bench.make_corpus_chunk(torch, c // bench.CHUNK, dev)[: min(bench.CHUNK, n - c)]
+        s = q[sub] @ rows.t()
+        d, i = torch.topk(s, k, dim=1)
+        best_d = torch.cat([best_d, d], 1)
+        best_i = torch.cat([best_i, i + c], 1)
+        d2, sel = torch.topk(best_d, k, dim=1)
+        best_d, best_i = d2, torch.gather(best_i, 1, sel)
+        del rows, s
+    ref_sets = [set(r.tolist()) for r in best_i]
+    got = I[sub].cpu()
+    recall = np.mean([len(ref_sets[r] & set(got[r].tolist())) / k for r in range(64)])
+    assert recall >= 0.999, recall
+    torch.testing.assert_close(D[sub], best_d, rtol=RTOL, atol=1e-3)
+    D2, I2 = index.search(q, k)
+    assert torch.equal(I, I2) and torch.equal(D, D2)
