@@ -295,6 +295,11 @@ def main():
             "launches_per_step": stats["filter_launches"], "peak_source": pk["source"],
             "peak_sustained": pk["bf16_sustained"],
             "frac_sustained": achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None}
+    tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tpath):   # dram bytes per corpus row from the committed ncu --set full capture
+        roof["traffic"] = json.load(open(tpath))["dram_bytes_per_corpus_row"] * n_local
+        roof["traffic_unit"] = "bytes per step (sum over the step's K1 launches; ncu dram read+write per row x rows)"
+        roof["algorithmic_bytes"] = n_local * DIM * 2 + nq * DIM * 2
     if roof["bound"] == "hbm":
         gbs = n_local * DIM * 2 / filt_s / 1e9 if filt_s > 0 else 0.0
         roof.update(achieved=gbs, peak=pk["hbm"], unit="GB/s", frac=gbs / pk["hbm"])

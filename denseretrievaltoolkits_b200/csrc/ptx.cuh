@@ -52,9 +52,10 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 // `bar` is a shared::cluster address (from mapa): arrive on another CTA's barrier
+// (plain arrive: an explicit .release.cluster here compiles to MEMBAR.ALL.GPU + CGAERRBAR per
+// call, which throttled the pair-mode pipeline to 1/3 of the tensor rate -- profiles/r1)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar)
-                 : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
