@@ -64,16 +64,20 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except Exception:
             self.proc = None
             return
         def pump():
             for line in self.proc.stdout:
-                self.rows.append(line.strip())
+                self.rows.append((time.time(), line.strip()))
         self.thread = threading.Thread(target=pump, daemon=True)
         self.thread.start()
+
+    def mark(self):
+        """Start of the timed region: earlier samples (warm-up, sampler start-up) are dropped."""
+        self.t0 = time.time()
 
     def stop(self):
         if not self.proc:
@@ -85,7 +89,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        t0 = getattr(self, "t0", 0.0)
+        t1 = time.time()
+        for ts, r in self.rows:
+            if ts < t0 or ts > t1:
+                continue
             f = [x.strip() for x in r.split(",")]
             if len(f) < 7:
                 continue
@@ -173,7 +181,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--nq", type=int, default=HEADLINE["nq"])
@@ -268,11 +276,12 @@ def main():
             ms = float(t.item())
         return ms, filt_ns, launches, index.search_stats()
 
-    for _ in range(max(args.warmup, 3)):
-        step_device()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                 # started before the warm-up so it is sampling by the timed region
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler.mark()
     ms, filt_ns, launches, stats = timed(step_device, args.steps)
     clocks = sampler.stop() if rank == 0 else None
     value = nq * args.steps / (ms / 1e3)

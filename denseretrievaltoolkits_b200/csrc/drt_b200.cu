@@ -473,7 +473,9 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
     cudaStream_t st = (cudaStream_t)stream;
     for (int i = 0; i < 8; ++i) s->stats[i] = 0;
 
-    int kctas = 1;
+    // CTA-pair tiles (M=256) halve the corpus-operand smem/L2 traffic per FLOP; with <= 128
+    // queries half of a pair tile would be padding and the pass is HBM-bound anyway.
+    int kctas = (nq > drt::kTileM) ? 2 : 1;
     if (const char* e = getenv("DRT_B200_CTAS")) kctas = (atoi(e) == 2) ? 2 : 1;
     if (flags & DRT_SEARCH_FORCE_1CTA) kctas = 1;
     if (flags & DRT_SEARCH_FORCE_2CTA) kctas = 2;
