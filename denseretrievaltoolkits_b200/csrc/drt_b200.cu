@@ -144,6 +144,7 @@ struct drt_store {
     std::vector<void*> seg_bf16;
     // search workspace (grow-only)
     DevBuf q_bf16, q_f32, thr, cnt, cand, seg_table, out_scores, out_ids, misc;
+    DevBuf qflag, sub_idx, sub_q, sub_os, sub_oi, sub_flag;   // exactness-check fallback
     int* err_host = nullptr;     // pinned + mapped: kernel watchdog code
     int* err_dev = nullptr;
     int64_t* misc_host = nullptr;  // pinned: [0] overflow flag [1] flagged count
@@ -174,7 +175,8 @@ int set_kernel_attrs(drt_store* s) {
 template <int kCtas>
 int launch_filter(const CUtensorMap& tq, const CUtensorMap& td, const drt::FilterParams& p, int sm_count,
                   cudaStream_t st) {
-    const int total = p.num_m_tiles * p.n_tile_count;
+    const int n_groups = (p.n_tile_count + p.unit_tiles - 1) / p.unit_tiles;
+    const int total = p.num_m_tiles * n_groups;                   // work units
     int clusters = std::min(sm_count / kCtas, total);
     if (clusters < 1) clusters = 1;
     cudaLaunchConfig_t cfg = {};
@@ -229,9 +231,10 @@ std::vector<Chunk> plan_chunks(int64_t ntotal, int64_t seg_rows, int cap, int ke
 
 // One query batch, all on device.  Returns DRT_OK, an error, or +1 = candidate overflow (retry).
 int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
-                 int64_t id_offset, uint32_t flags, cudaStream_t st, int attempt, int kctas) {
+                 int64_t id_offset, uint32_t flags, cudaStream_t st, int attempt, int kctas,
+                 int keep_override, unsigned char* qflag, int64_t* flagged_out) {
     const int dim = s->dim;
-    const int keep = kprime_for(k);
+    const int keep = keep_override > 0 ? keep_override : kprime_for(k);
     int cap = next_pow2(std::max(4 * keep, 4096));
     if (attempt >= 1) cap *= 4;
     if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
@@ -280,6 +283,12 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         p.num_m_tiles = (int)((nq + drt::kTileM * kctas - 1) / (drt::kTileM * kctas));
         p.n_tile_begin = (int)(c.row0 / drt::kTileN);
         p.n_tile_count = (int)((c.row1 + drt::kTileN - 1) / drt::kTileN) - p.n_tile_begin;
+        // corpus tiles per work unit: 16 when the launch is large, fewer for the small early
+        // chunks so that every CTA (pair) still gets at least ~4 units
+        p.unit_tiles = 16;
+        while (p.unit_tiles > 1 &&
+               (int64_t)p.num_m_tiles * ((p.n_tile_count + p.unit_tiles - 1) / p.unit_tiles) < 4ll * (s->sm_count / kctas))
+            p.unit_tiles /= 2;
         p.num_k_blocks = dim / drt::kBlockK;
         p.nq = (int)nq;
         p.rows_valid = (uint32_t)c.row1;    // rows past this chunk's end are not admitted yet
@@ -308,7 +317,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         drt::rescore_kernel<<<(int)nq, 256, smem, st>>>(cand, cnt, (uint32_t)cap, (uint32_t)keep, q_dev, dim,
                                                        (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
                                                        (long long)id_offset, out_s, (long long*)out_i,
-                                                       (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged);
+                                                       (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag);
         s->stats[0] += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -320,14 +329,66 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         return fail(code ? DRT_E_INTERNAL : DRT_E_CUDA, "search kernels failed: %s (watchdog code %d)",
                     cudaGetErrorString(e), code);
     }
-    s->stats[3] = keep;
-    s->stats[5] = kctas;
+    if (keep_override == 0) { s->stats[3] = keep; s->stats[5] = kctas; }
     for (size_t i = 0; i < n_timed; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]) == cudaSuccess) s->stats[7] += (int64_t)(ms * 1e6);
     }
     if ((int)(s->misc_host[0] & 0xffffffff) != 0) return 1;   // overflow -> caller retries
-    s->stats[4] += (int64_t)s->misc_host[1];
+    if (flagged_out) *flagged_out = (int64_t)s->misc_host[1];
+    return DRT_OK;
+}
+
+// search_batch + the overflow retry ladder (bigger buffer / growth 2, then fixed chunks)
+int search_retrying(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
+                    int64_t id_offset, uint32_t flags, cudaStream_t st, int kctas, int keep_override,
+                    unsigned char* qflag, int64_t* flagged_out) {
+    for (int attempt = 0;; ++attempt) {
+        const int rc = search_batch(s, q_dev, nq, k, out_s, out_i, id_offset, flags, st, attempt, kctas,
+                                    keep_override, qflag, flagged_out);
+        if (rc <= 0) return rc;
+        s->stats[2] += 1;
+        if (attempt >= 2) return fail(DRT_E_INTERNAL, "candidate buffer overflow persisted after retries");
+    }
+}
+
+// Queries whose exactness check flagged are searched again with a doubled candidate count k'
+// (up to 3 rounds); what is still flagged afterwards is reported in stats[4].
+int refine_flagged(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
+                   int64_t id_offset, uint32_t flags, cudaStream_t st, unsigned char* qflag, int64_t* flagged) {
+    int keep = kprime_for(k);
+    std::vector<unsigned char> hflag;
+    std::vector<int> idx;
+    for (int round = 0; *flagged > 0 && round < 3 && keep * 2 <= 4096; ++round) {
+        keep *= 2;
+        hflag.resize((size_t)nq);
+        CUDA_TRY(cudaMemcpyAsync(hflag.data(), qflag, (size_t)nq, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        idx.clear();
+        for (int64_t i = 0; i < nq; ++i) if (hflag[i]) idx.push_back((int)i);
+        const int64_t nf = (int64_t)idx.size();
+        if (nf == 0) break;
+        int rc;
+        if ((rc = s->sub_idx.ensure((size_t)nf * 4)) != DRT_OK) return rc;
+        if ((rc = s->sub_q.ensure((size_t)nf * s->dim * 4)) != DRT_OK) return rc;
+        if ((rc = s->sub_os.ensure((size_t)nf * k * 4)) != DRT_OK) return rc;
+        if ((rc = s->sub_oi.ensure((size_t)nf * k * 8)) != DRT_OK) return rc;
+        if ((rc = s->sub_flag.ensure((size_t)nf)) != DRT_OK) return rc;
+        CUDA_TRY(cudaMemcpyAsync(s->sub_idx.p, idx.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+        drt::gather_rows_kernel<<<(int)std::min<int64_t>(nf, 4096), 192, 0, st>>>(
+            q_dev, (const int*)s->sub_idx.p, (float*)s->sub_q.p, s->dim, (int)nf);
+        int64_t still = 0;
+        const int kctas = (flags & DRT_SEARCH_FORCE_1CTA) ? 1 : (flags & DRT_SEARCH_FORCE_2CTA) ? 2 : (nf > drt::kTileM ? 2 : 1);
+        rc = search_retrying(s, (const float*)s->sub_q.p, nf, k, (float*)s->sub_os.p, (int64_t*)s->sub_oi.p, id_offset,
+                             flags, st, kctas, keep, (unsigned char*)s->sub_flag.p, &still);
+        if (rc != DRT_OK) return rc;
+        drt::scatter_results_kernel<<<(int)std::min<int64_t>(nf, 4096), 128, 0, st>>>(
+            (const float*)s->sub_os.p, (const long long*)s->sub_oi.p, (const unsigned char*)s->sub_flag.p,
+            (const int*)s->sub_idx.p, out_s, (long long*)out_i, qflag, k, (int)nf);
+        CUDA_TRY(cudaGetLastError());
+        s->stats[0] += 2;
+        *flagged = still;
+    }
     return DRT_OK;
 }
 
@@ -385,6 +446,7 @@ int drt_store_destroy(drt_store* s) {
     for (void* p : s->seg_bf16) cudaFree(p);
     s->q_bf16.release(); s->q_f32.release(); s->thr.release(); s->cnt.release(); s->cand.release();
     s->seg_table.release(); s->out_scores.release(); s->out_ids.release(); s->misc.release();
+    s->qflag.release(); s->sub_idx.release(); s->sub_q.release(); s->sub_os.release(); s->sub_oi.release(); s->sub_flag.release();
     if (s->err_host) cudaFreeHost(s->err_host);
     if (s->misc_host) cudaFreeHost(s->misc_host);
     (void)cudaGetLastError();
@@ -505,13 +567,14 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
                 os_dev, (long long*)oi_dev, (size_t)nb * k);
             CUDA_TRY(cudaGetLastError());
         } else {
-            int attempt = 0;
-            for (;;) {
-                rc = search_batch(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, attempt, kctas);
-                if (rc <= 0) break;
-                s->stats[2] += 1;
-                if (++attempt > 2) return fail(DRT_E_INTERNAL, "candidate buffer overflow persisted after retries");
+            if ((rc = s->qflag.ensure((size_t)nb)) != DRT_OK) return rc;
+            int64_t flagged = 0;
+            rc = search_retrying(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, kctas, 0,
+                                 (unsigned char*)s->qflag.p, &flagged);
+            if (rc == DRT_OK && flagged > 0 && !(flags & DRT_SEARCH_NO_RESCORE)) {
+                rc = refine_flagged(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, (unsigned char*)s->qflag.p, &flagged);
             }
+            s->stats[4] += flagged;
             if (rc != DRT_OK) return rc;
         }
         if (!io_on_device) {

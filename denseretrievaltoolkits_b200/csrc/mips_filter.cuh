@@ -7,8 +7,9 @@
 // segment.  The kernel never writes the score matrix.  Queries sit on the MMA M dimension, so an
 // accumulator row (= one TMEM lane) belongs to one query and ONE epilogue thread owns it: that
 // thread keeps the query's current admission threshold in a register, streams the 256 scores of
-// its lane out of TMEM with tcgen05.ld, and only when a score beats the threshold appends
-// (score,row) to the query's candidate list in global memory (rare: O(k log N) per query).
+// its lane out of TMEM with tcgen05.ld, and only when a score beats the threshold stages
+// (score,row) in shared memory; staged candidates are appended to the query's list in global
+// memory with one atomicAdd per flush (rare: O(k log N) candidates per query per search).
 //
 // Roles inside a CTA (192 threads):
 //   warp 0    TMA producer: streams 128x64 query k-blocks and 256x64 (128x64 per CTA in pair
@@ -19,11 +20,14 @@
 //   warps 2-5 epilogue: one warp per TMEM lane quarter; overlaps with the MMA of the next tile
 //             through the second accumulator stage.
 // kCtas = 2 runs the same protocol on a CTA pair (cta_group::2): each CTA owns 128 queries and
-// loads half of every corpus tile, halving L2->SM operand traffic per FLOP.
+// loads half of every corpus tile, halving the corpus-operand smem/L2 traffic per FLOP.
 //
-// Tiles are walked persistently, query-tile fastest, so the CTAs resident at any moment share
-// the same few corpus tiles (one HBM read, L2 hits for the rest) while the whole bf16 query
-// matrix stays L2 resident.
+// Work decomposition: a UNIT is one query tile x `unit_tiles` consecutive corpus tiles; units
+// are numbered query-tile-fastest and dealt round-robin to the persistent CTAs.  The CTAs
+// resident at any moment therefore work on the same few groups of corpus tiles (each tile leaves
+// HBM once and is served from L2 to the other query tiles) while the bf16 query matrix stays L2
+// resident, and an epilogue thread keeps one query (threshold in a register, staged candidates
+// in smem) for a whole unit.
 #pragma once
 #include "ptx.cuh"
 
@@ -33,14 +37,16 @@ constexpr int kTileM = 128;     // queries per CTA
 constexpr int kTileN = 256;     // corpus rows per tile (per CTA pair in pair mode)
 constexpr int kBlockK = 64;     // bf16 elements per k-block = one 128-byte swizzle span
 constexpr int kFilterThreads = 192;
+constexpr int kStageSlots = 16; // staged candidates per epilogue thread before a flush
 
 struct FilterParams {
     int num_m_tiles;        // ceil(nq / (128 * kCtas))
     int n_tile_begin;       // first 256-row tile of this launch, relative to the segment
     int n_tile_count;
+    int unit_tiles;         // corpus tiles per work unit
     int num_k_blocks;       // dim / 64
     int nq;
-    uint32_t rows_valid;    // rows present in this segment
+    uint32_t rows_valid;    // rows of this segment that may be admitted by this launch
     uint32_t row_base;      // store row id of the segment's first row
     uint32_t cap;           // candidate slots per query
     const float* thr;       // [nq] admission threshold (strict >)
@@ -70,8 +76,10 @@ struct FilterCfg {
     static constexpr uint32_t kBRows = kTileN / kCtas;                    // rows this CTA loads
     static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;             // 32 KB | 16 KB
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    static constexpr uint32_t kBarBytes = (2 * kStages + 4) * 8 + 16;
-    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + 1024;  // + align slack
+    static constexpr uint32_t kBarBytes = 256;                            // (2*kStages+4) mbarriers + tmem holder
+    static constexpr uint32_t kStagingBytes = kStageSlots * kTileM * 8;   // 16 KB candidate staging
+    static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024;
+    static_assert((2 * kStages + 4) * 8 + 8 <= kBarBytes, "barrier block too small");
 };
 
 // wait for all outstanding tcgen05.ld; the register operands tie later uses to this point
@@ -87,28 +95,47 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
                  : "memory");
 }
 
-// Filter 32 consecutive scores of one query (registers v) against thr.
-__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr, uint32_t row0,
+// Append this thread's `n` staged candidates (smem slots my_stage + i*1024) to query q's list.
+__device__ __noinline__ void flush_staging(uint32_t my_stage, uint32_t n, const FilterParams& p, int q) {
+    const uint32_t base = atomicAdd(p.cnt + q, n);
+    uint64_t* dst = p.cand + static_cast<size_t>(q) * p.cap;
+    for (uint32_t i = 0; i < n; ++i) {
+        uint64_t key;
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(key) : "r"(my_stage + i * (kTileM * 8)));
+        if (base + i < p.cap) dst[base + i] = key;
+    }
+}
+
+// Filter 32 consecutive scores of one query (registers v) against thr.  `row_id0` is the store
+// row id of v[0]; only the first `nvalid` columns exist in the corpus.
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr, uint32_t row_id0,
+                                             int nvalid, uint32_t my_stage, uint32_t& scnt,
                                              const FilterParams& p, int q) {
-    float m = __uint_as_float(v[0]);
+    // maxima of the four 8-column sub-blocks: the warp only walks a sub-block in which some
+    // lane has a hit, so the admission cost stays proportional to the (rare) hits
+    float mb[4];
 #pragma unroll
-    for (int j = 1; j < 32; ++j) m = fmaxf(m, __uint_as_float(v[j]));
-    if (m > thr) {  // rare once the threshold has warmed up
-        uint32_t hit = 0;
+    for (int b = 0; b < 4; ++b) {
+        float m = __uint_as_float(v[8 * b]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-            const bool h = (__uint_as_float(v[j]) > thr) && (row0 + j < p.rows_valid);
-            hit |= (h ? 1u : 0u) << j;
-        }
-        if (hit) {
-            uint32_t slot = atomicAdd(p.cnt + q, __popc(hit));
-            uint64_t* dst = p.cand + static_cast<size_t>(q) * p.cap;
+        for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * b + j]));
+        mb[b] = m;
+    }
+    if (fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) > thr) {  // rare once the threshold warmed up
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                if (hit & (1u << j)) {
-                    if (slot < p.cap)
-                        dst[slot] = pack_key(__uint_as_float(v[j]), p.row_base + row0 + j);
-                    ++slot;
+        for (int b = 0; b < 4; ++b) {
+            if (mb[b] > thr) {
+#pragma unroll
+                for (int j = 8 * b; j < 8 * b + 8; ++j) {
+                    const float f = __uint_as_float(v[j]);
+                    if (f > thr && j < nvalid) {
+                        const uint64_t key = pack_key(f, row_id0 + j);
+                        asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * (kTileM * 8)), "l"(key) : "memory");
+                        if (++scnt == kStageSlots) {
+                            flush_staging(my_stage, kStageSlots, p, q);
+                            scnt = 0;
+                        }
+                    }
                 }
             }
         }
@@ -131,6 +158,7 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
     // ---- shared memory carve-up (shared::cta addresses; tiles 1024-byte aligned) ----
     const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bars = base + kStages * Cfg::kStageBytes;
+    const uint32_t staging = bars + Cfg::kBarBytes;
     auto smem_a = [&](int s) { return base + s * Cfg::kStageBytes; };
     auto smem_b = [&](int s) { return base + s * Cfg::kStageBytes + Cfg::kABytes; };
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -165,7 +193,8 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
 
     const int cluster_id = blockIdx.x / kCtas;
     const int num_clusters = gridDim.x / kCtas;
-    const int total_tiles = p.num_m_tiles * p.n_tile_count;
+    const int n_groups = (p.n_tile_count + p.unit_tiles - 1) / p.unit_tiles;
+    const int num_units = p.num_m_tiles * n_groups;
     const int nkb = p.num_k_blocks;
 
     if (warp == 0) {
@@ -173,30 +202,33 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
         if (ptx::elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-                const int m_tile = t % p.num_m_tiles;
-                const int n_tile = p.n_tile_begin + t / p.num_m_tiles;
+            for (int u = cluster_id; u < num_units; u += num_clusters) {
+                const int m_tile = u % p.num_m_tiles;
+                const int nt0 = (u / p.num_m_tiles) * p.unit_tiles;
+                const int nt1 = min(nt0 + p.unit_tiles, p.n_tile_count);
                 const int q_row = (m_tile * kCtas + static_cast<int>(rank)) * kTileM;
-                const int d_row = n_tile * kTileN + static_cast<int>(rank) * Cfg::kBRows;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 101);
-                    if constexpr (kCtas == 1) {
-                        ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
-                        ptx::tma_load_2d(smem_a(stage), &tmap_q, full_bar(stage), kb * kBlockK,
-                                         q_row, ptx::kEvictLast);
-                        ptx::tma_load_2d(smem_b(stage), &tmap_d, full_bar(stage), kb * kBlockK,
-                                         d_row, ptx::kEvictNormal);
-                    } else {
-                        // both CTAs signal the LEADER's full barrier
-                        const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
-                        ptx::tma_load_2d_pair(smem_a(stage), &tmap_q, lead_full, kb * kBlockK,
-                                              q_row, ptx::kEvictLast);
-                        ptx::tma_load_2d_pair(smem_b(stage), &tmap_d, lead_full, kb * kBlockK,
-                                              d_row, ptx::kEvictNormal);
-                        if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
-                        else           ptx::mbar_arrive_cluster(lead_full);
+                for (int nt = nt0; nt < nt1; ++nt) {
+                    const int d_row = (p.n_tile_begin + nt) * kTileN + static_cast<int>(rank) * Cfg::kBRows;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        ptx::mbar_wait(empty_bar(stage), phase ^ 1u, p.err, 101);
+                        if constexpr (kCtas == 1) {
+                            ptx::mbar_arrive_expect_tx(full_bar(stage), Cfg::kStageBytes);
+                            ptx::tma_load_2d(smem_a(stage), &tmap_q, full_bar(stage), kb * kBlockK,
+                                             q_row, ptx::kEvictLast);
+                            ptx::tma_load_2d(smem_b(stage), &tmap_d, full_bar(stage), kb * kBlockK,
+                                             d_row, ptx::kEvictNormal);
+                        } else {
+                            // both CTAs signal the LEADER's full barrier
+                            const uint32_t lead_full = ptx::mapa(full_bar(stage), 0);
+                            ptx::tma_load_2d_pair(smem_a(stage), &tmap_q, lead_full, kb * kBlockK,
+                                                  q_row, ptx::kEvictLast);
+                            ptx::tma_load_2d_pair(smem_b(stage), &tmap_d, lead_full, kb * kBlockK,
+                                                  d_row, ptx::kEvictNormal);
+                            if (rank == 0) ptx::mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::kStageBytes);
+                            else           ptx::mbar_arrive_cluster(lead_full);
+                        }
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -207,27 +239,31 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1u;
-                ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 102);
-                ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * kTileN;
-                for (int kb = 0; kb < nkb; ++kb) {
-                    ptx::mbar_wait(full_bar(stage), phase, p.err, 103);
+            for (int u = cluster_id; u < num_units; u += num_clusters) {
+                const int nt0 = (u / p.num_m_tiles) * p.unit_tiles;
+                const int nt1 = min(nt0 + p.unit_tiles, p.n_tile_count);
+                for (int nt = nt0; nt < nt1; ++nt, ++it) {
+                    const int acc = it & 1;
+                    const uint32_t acc_phase = (it >> 1) & 1u;
+                    ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u, p.err, 102);
                     ptx::tc_fence_after();
-                    const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a(stage));
-                    const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b(stage));
+                    const uint32_t d_tmem = tmem_base + acc * kTileN;
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        ptx::mbar_wait(full_bar(stage), phase, p.err, 103);
+                        ptx::tc_fence_after();
+                        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(smem_a(stage));
+                        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(smem_b(stage));
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes (= 16 bf16) along K inside the swizzle span: +2 in the
-                        // 16-byte-granular start-address field
-                        ptx::umma_bf16<kCtas>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
-                                              (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // +32 bytes (= 16 bf16) along K inside the swizzle span: +2 in the
+                            // 16-byte-granular start-address field
+                            ptx::umma_bf16<kCtas>(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc,
+                                                  (kb | k) != 0 ? 1u : 0u);
+                        }
+                        ptx::umma_commit<kCtas>(empty_bar(stage));      // smem slot free when read
+                        if (kb == nkb - 1) ptx::umma_commit<kCtas>(tfull_bar(acc));  // accumulator done
+                        if (++stage == kStages) { stage = 0; phase ^= 1u; }
                     }
-                    ptx::umma_commit<kCtas>(empty_bar(stage));      // smem slot free when read
-                    if (kb == nkb - 1) ptx::umma_commit<kCtas>(tfull_bar(acc));  // accumulator done
-                    if (++stage == kStages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -235,43 +271,53 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
         // ================================ epilogue ====================================
         const uint32_t quarter = warp & 3u;   // TMEM lanes [32*quarter, +32) belong to this warp
         const uint32_t lead_tempty0 = (kCtas == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
+        const uint32_t my_stage = staging + (quarter * 32u + lane) * 8u;
+        uint32_t scnt = 0;
         int it = 0;
-        for (int t = cluster_id; t < total_tiles; t += num_clusters, ++it) {
-            const int m_tile = t % p.num_m_tiles;
-            const int n_tile = p.n_tile_begin + t / p.num_m_tiles;
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1u;
+        for (int u = cluster_id; u < num_units; u += num_clusters) {
+            const int m_tile = u % p.num_m_tiles;
+            const int nt0 = (u / p.num_m_tiles) * p.unit_tiles;
+            const int nt1 = min(nt0 + p.unit_tiles, p.n_tile_count);
             const int q = (m_tile * kCtas + static_cast<int>(rank)) * kTileM + quarter * 32 + lane;
             const float thr = (q < p.nq) ? p.thr[q] : __int_as_float(0x7f800000);
             const int qc = (q < p.nq) ? q : 0;
+            for (int nt = nt0; nt < nt1; ++nt, ++it) {
+                const int acc = it & 1;
+                const uint32_t acc_phase = (it >> 1) & 1u;
+                const uint32_t row0 = static_cast<uint32_t>(p.n_tile_begin + nt) * kTileN;
+                const int valid_cols = static_cast<int>(min(p.rows_valid - row0, static_cast<uint32_t>(kTileN)));
+                ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err, 104);
+                ptx::tc_fence_after();
 
-            ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err, 104);
-            ptx::tc_fence_after();
-
-            const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN;
-            const uint32_t row0 = static_cast<uint32_t>(n_tile) * kTileN;
-            uint32_t va[32], vb[32];
-            ptx::tmem_ld_32x32(taddr, va);
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN;
+                uint32_t va[32], vb[32];
+                ptx::tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-            for (int c = 0; c < kTileN / 32; c += 2) {
-                tmem_ld_wait_regs(va);
-                ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-                filter_chunk(va, thr, row0 + c * 32, p, qc);
-                tmem_ld_wait_regs(vb);
-                if (c + 2 < kTileN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                filter_chunk(vb, thr, row0 + (c + 1) * 32, p, qc);
-            }
-            // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if constexpr (kCtas == 1) {
-                    ptx::mbar_arrive(tempty_bar(acc));
-                } else {
-                    if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
-                    else           ptx::mbar_arrive_cluster(lead_tempty0 + 8u * acc);
+                for (int c = 0; c < kTileN / 32; c += 2) {
+                    tmem_ld_wait_regs(va);
+                    ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                    filter_chunk(va, thr, p.row_base + row0 + c * 32, valid_cols - c * 32, my_stage, scnt, p, qc);
+                    tmem_ld_wait_regs(vb);
+                    if (c + 2 < kTileN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                    filter_chunk(vb, thr, p.row_base + row0 + (c + 1) * 32, valid_cols - (c + 1) * 32, my_stage, scnt, p, qc);
+                }
+                // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
+                ptx::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (kCtas == 1) {
+                        ptx::mbar_arrive(tempty_bar(acc));
+                    } else {
+                        if (rank == 0) ptx::mbar_arrive(tempty_bar(acc));
+                        else           ptx::mbar_arrive_cluster(lead_tempty0 + 8u * acc);
+                    }
                 }
             }
+            if (scnt) {   // the next unit belongs to another query: publish what is staged
+                flush_staging(my_stage, scnt, p, qc);
+                scnt = 0;
+            }
+            __syncwarp();
         }
     }
 

@@ -43,25 +43,83 @@ __global__ void init_query_state_kernel(float* thr, uint32_t* cnt, int nq) {
 // keep the best `keep` (score desc, row asc) and publish the keep-th score as the new admission
 // threshold.  Chunks are visited in ascending row order and admission is strict (>), so a later
 // row that ties the threshold loses to the earlier one — the same outcome as faiss' heap.
+//
+// Selection is an MSD radix select on the packed 64-bit keys (8 bits per pass, 256-bin smem
+// histogram, warp-parallel suffix scan to locate the bin holding the keep-th largest key), O(n)
+// work per query instead of the O(n log^2 n) of a full sort; keys are unique (the row id is part
+// of the key), so exactly `keep` keys are >= the pivot.  Survivors are written back unordered:
+// neither the filter kernel nor later selects need order, and K2 sorts its own output.
 __global__ void __launch_bounds__(256)
 select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t keep,
               int* overflow) {
     extern __shared__ uint64_t s_keys[];
+    __shared__ uint32_t s_hist[256];
+    __shared__ uint32_t s_bin, s_need, s_bucket, s_out;
+    __shared__ uint64_t s_pivot;
     const int q = blockIdx.x;
+    const int tid = threadIdx.x;
     uint32_t n = cnt[q];
     if (n > cap) {                       // appends were dropped: the host must redo the search
-        if (threadIdx.x == 0) *overflow = 1;
+        if (tid == 0) *overflow = 1;
         n = cap;
     }
     if (n <= keep) return;
-    const int P = next_pow2_dev(static_cast<int>(n));
     uint64_t* row = cand + static_cast<size_t>(q) * cap;
-    for (int i = threadIdx.x; i < P; i += blockDim.x) s_keys[i] = (i < static_cast<int>(n)) ? row[i] : 0ull;
-    bitonic_sort_desc_u64(s_keys, P);
-    for (int i = threadIdx.x; i < static_cast<int>(keep); i += blockDim.x) row[i] = s_keys[i];
-    if (threadIdx.x == 0) {
+    for (uint32_t i = tid; i < n; i += blockDim.x) s_keys[i] = row[i];
+    if (tid == 0) { s_need = keep; s_out = 0; }
+    uint64_t prefix = 0, mask = 0;
+    bool found = false;
+    for (int shift = 56; shift >= 0 && !found; shift -= 8) {
+        s_hist[tid] = 0;                 // blockDim.x == 256
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            const uint64_t key = s_keys[i];
+            if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFF], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane l owns bins [8l, 8l+8); suffix-scan the lane sums to find the bin (from the
+            // top) at which the running count reaches `need`
+            const uint32_t need = s_need;
+            uint32_t h[8], s = 0;
+#pragma unroll
+            for (int b = 0; b < 8; ++b) { h[b] = s_hist[tid * 8 + b]; s += h[b]; }
+            uint32_t v = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_down_sync(0xffffffffu, v, o);
+                if (tid + o < 32) v += t;
+            }
+            const uint32_t above = v - s;          // keys in bins of higher lanes
+            if (above < need && need <= above + s) {
+                uint32_t cum = above;
+#pragma unroll
+                for (int b = 7; b >= 0; --b) {
+                    if (cum < need && need <= cum + h[b]) { s_bin = tid * 8 + b; s_need = need - cum; s_bucket = h[b]; }
+                    cum += h[b];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= static_cast<uint64_t>(s_bin) << shift;
+        mask |= 0xFFull << shift;
+        if (s_bucket == 1) {             // a single key carries this prefix: it is the pivot
+            for (uint32_t i = tid; i < n; i += blockDim.x) {
+                const uint64_t key = s_keys[i];
+                if ((key & mask) == prefix) s_pivot = key;
+            }
+            found = true;
+        }
+        __syncthreads();
+    }
+    const uint64_t pivot = found ? s_pivot : prefix;
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+        const uint64_t key = s_keys[i];
+        if (key >= pivot) row[atomicAdd(&s_out, 1u)] = key;
+    }
+    if (tid == 0) {
         cnt[q] = keep;
-        thr[q] = ordered_to_float(static_cast<uint32_t>(s_keys[keep - 1] >> 32));
+        thr[q] = ordered_to_float(static_cast<uint32_t>(pivot >> 32));
     }
 }
 
@@ -72,7 +130,7 @@ __global__ void __launch_bounds__(256)
 rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t keep,
                const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
                int k, long long id_offset, float* out_scores, long long* out_ids,
-               int do_rescore, unsigned long long* flagged) {
+               int do_rescore, unsigned long long* flagged, unsigned char* qflag) {
     extern __shared__ uint64_t s_keys[];            // [P] then dim floats
     const int q = blockIdx.x;
     const int n = static_cast<int>(min(min(cnt[q], cap), keep));
@@ -132,11 +190,35 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
     // Exactness check: rows that never became candidates have bf16 score <= a_min.  If the
     // candidate list was full and a_min plus twice the largest observed bf16 error reaches the
     // exact k-th score, a non-candidate could belong to the top-k: count the query as flagged.
-    if (threadIdx.x == 0 && do_rescore && n == static_cast<int>(keep) && n >= k && s_keys[k - 1] != 0ull) {
-        const float tau = ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32));
-        const float amin = ordered_to_float(s_amin);
-        const float emax = __uint_as_float(s_emax);
-        if (amin + 2.f * emax >= tau) atomicAdd(flagged, 1ull);
+    if (threadIdx.x == 0) {
+        bool flag = false;
+        if (do_rescore && n == static_cast<int>(keep) && n >= k && s_keys[k - 1] != 0ull) {
+            const float tau = ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32));
+            const float amin = ordered_to_float(s_amin);
+            const float emax = __uint_as_float(s_emax);
+            flag = amin + 2.f * emax >= tau;
+        }
+        if (flag) atomicAdd(flagged, 1ull);
+        if (qflag) qflag[q] = flag ? 1 : 0;
+    }
+}
+
+// Fallback plumbing: pull the flagged queries into a dense sub-batch / put their results back.
+__global__ void gather_rows_kernel(const float* __restrict__ src, const int* __restrict__ idx,
+                                   float* __restrict__ dst, int dim, int n) {
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const float4* s4 = reinterpret_cast<const float4*>(src + static_cast<size_t>(idx[r]) * dim);
+        float4* d4 = reinterpret_cast<float4*>(dst + static_cast<size_t>(r) * dim);
+        for (int j = threadIdx.x; j < (dim >> 2); j += blockDim.x) d4[j] = s4[j];
+    }
+}
+__global__ void scatter_results_kernel(const float* __restrict__ ss, const long long* __restrict__ si,
+                                       const unsigned char* __restrict__ sf, const int* __restrict__ idx,
+                                       float* os, long long* oi, unsigned char* qf, int k, int n) {
+    for (int r = blockIdx.x; r < n; r += gridDim.x) {
+        const size_t d = static_cast<size_t>(idx[r]) * k, s = static_cast<size_t>(r) * k;
+        for (int j = threadIdx.x; j < k; j += blockDim.x) { os[d + j] = ss[s + j]; oi[d + j] = si[s + j]; }
+        if (threadIdx.x == 0) qf[idx[r]] = sf[r];
     }
 }
 
