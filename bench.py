@@ -244,7 +244,7 @@ def main():
             dist.all_gather(Ds, D)
             dist.all_gather(Is, I)
             from denseretrievaltoolkits_b200.store import _cuda_merge
-            return _cuda_merge(torch.stack(Ds), torch.stack(Is), k)
+            return _cuda_merge(torch.stack(Ds), torch.stack(Is), k, sorted_unique=True)
         return index.search(q_dev, k, flags=flags)
 
     def step_host():

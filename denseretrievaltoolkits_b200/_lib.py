@@ -33,6 +33,8 @@ SEARCH_NO_RESCORE = 1
 SEARCH_FORCE_1CTA = 2
 SEARCH_FORCE_2CTA = 4
 SEARCH_TIME_KERNELS = 8
+MERGE_DEFAULT = 0
+MERGE_SORTED_UNIQUE = 1
 MAX_K = 2048
 
 _lib = None
@@ -90,7 +92,7 @@ def load() -> ctypes.CDLL:
     lib.drt_plan_params.argtypes = [c_int, c_int, POINTER(c_int), POINTER(c_int)]
     lib.drt_plan_chunks.argtypes = [c_int64, c_int64, c_int, c_int, i64p, c_int]
     lib.drt_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
-                                   c_void_p, c_int, c_void_p]
+                                   c_void_p, c_uint32, c_int, c_void_p]
     lib.drt_inbatch_ce_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                        c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]

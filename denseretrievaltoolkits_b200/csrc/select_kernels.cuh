@@ -307,6 +307,66 @@ merge_topk_kernel(int G, const float* scores, const long long* ids, long long nq
     }
 }
 
+// K3, fast path for the row-sharded store: every input list is already in canonical order
+// (score desc, id asc) and the shards hold disjoint id ranges, so no id can repeat.  Each entry's
+// output position is then its merge rank = (position in its own list) + sum over the other lists
+// of (entries that precede it), found by binary search: O(G*k*G*log k) per query, no sort.
+__device__ __forceinline__ bool merge_precedes(float sa, long long ia, float sb, long long ib) {
+    return sa > sb || (sa == sb && static_cast<unsigned long long>(ia) < static_cast<unsigned long long>(ib));
+}
+
+__global__ void __launch_bounds__(256)
+merge_sorted_kernel(int G, const float* scores, const long long* ids, long long nq, int k_in,
+                    int k_out, float* out_scores, long long* out_ids) {
+    extern __shared__ uint64_t s_raw[];
+    const long long q = blockIdx.x;
+    const int n = G * k_in;
+    long long* s_id = reinterpret_cast<long long*>(s_raw);
+    float* s_sc = reinterpret_cast<float*>(s_id + n);
+    __shared__ int s_valid;
+    if (threadIdx.x == 0) s_valid = 0;
+    __syncthreads();
+    int local_valid = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int g = i / k_in, j = i - g * k_in;
+        const size_t o = (static_cast<size_t>(g) * nq + q) * k_in + j;
+        float sc = scores[o];
+        long long id = ids[o];
+        if (id < 0 || !(sc > -FLT_MAX)) { id = -1; sc = -FLT_MAX; } else ++local_valid;
+        s_id[i] = id; s_sc[i] = sc;
+    }
+    if (local_valid) atomicAdd(&s_valid, local_valid);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long id = s_id[i];
+        if (id < 0) continue;                      // padding sits at list tails and is never placed
+        const float sc = s_sc[i];
+        const int g = i / k_in;
+        int rank = i - g * k_in;
+        for (int h = 0; h < G; ++h) {
+            if (h == g) continue;
+            int lo = 0, hi = k_in;                 // first position in list h that does not precede us
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const long long im = s_id[h * k_in + mid];
+                if (im >= 0 && merge_precedes(s_sc[h * k_in + mid], im, sc, id)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) {
+            const size_t o = static_cast<size_t>(q) * k_out + rank;
+            out_scores[o] = sc;
+            out_ids[o] = id;
+        }
+    }
+    const int valid = s_valid;
+    for (int i = valid + threadIdx.x; i < k_out; i += blockDim.x) {
+        const size_t o = static_cast<size_t>(q) * k_out + i;
+        out_scores[o] = -FLT_MAX;
+        out_ids[o] = -1;
+    }
+}
+
 // Mining filter (process_sample, DRT/trainer/sampler.py:69-80): one warp per query, ballot
 // compaction keeps rank order.
 __global__ void filter_negatives_kernel(const long long* ids, long long nq, int k,

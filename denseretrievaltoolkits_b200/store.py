@@ -25,8 +25,9 @@ import torch.distributed as dist
 from . import _lib
 
 
-def _cuda_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
-    """scores/ids: CUDA tensors [G, Q, k_in] -> (D [Q,k_out], I [Q,k_out]) via drt_merge_topk."""
+def _cuda_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int, sorted_unique: bool = False):
+    """scores/ids: CUDA tensors [G, Q, k_in] -> (D [Q,k_out], I [Q,k_out]) via drt_merge_topk.
+    `sorted_unique`: the lists are per-shard search results (ordered, disjoint ids)."""
     if not scores.is_cuda:
         raise RuntimeError("merge needs CUDA tensors: there is no CPU fallback")
     lib = _lib.load()
@@ -37,8 +38,8 @@ def _cuda_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
     # the kernel merges <= 8192 entries per query: fold lists hierarchically above that
     while G * k_in > 8192 and G > 1:
         half = (G + 1) // 2
-        d0, i0 = _cuda_merge(scores[:half], ids[:half], min(k_out, half * k_in))
-        d1, i1 = _cuda_merge(scores[half:], ids[half:], min(k_out, (G - half) * k_in))
+        d0, i0 = _cuda_merge(scores[:half], ids[:half], min(k_out, half * k_in), sorted_unique)
+        d1, i1 = _cuda_merge(scores[half:], ids[half:], min(k_out, (G - half) * k_in), sorted_unique)
         kk = max(d0.shape[1], d1.shape[1])
         pad = lambda d, i: (torch.nn.functional.pad(d, (0, kk - d.shape[1]), value=-3.4028234663852886e38),
                             torch.nn.functional.pad(i, (0, kk - i.shape[1]), value=-1))
@@ -49,7 +50,8 @@ def _cuda_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int):
     D = torch.empty((Q, k_out), dtype=torch.float32, device=dev)
     I = torch.empty((Q, k_out), dtype=torch.int64, device=dev)
     _lib.check(lib.drt_merge_topk(G, scores.data_ptr(), ids.data_ptr(), Q, k_in, k_out, D.data_ptr(),
-                                  I.data_ptr(), dev.index, _lib.current_stream_ptr(dev.index)), "merge_topk")
+                                  I.data_ptr(), _lib.MERGE_SORTED_UNIQUE if sorted_unique else _lib.MERGE_DEFAULT,
+                                  dev.index, _lib.current_stream_ptr(dev.index)), "merge_topk")
     return D, I
 
 
@@ -74,7 +76,8 @@ class ShardedCorpusStore:
             from .faiss_compat import IndexFlatIP
 
             index_factory = lambda: IndexFlatIP(self.d, device=device, seg_rows=seg_rows)
-        self._merge = merge_fn or _cuda_merge
+        # shard results are ordered and id-disjoint: use the rank-based merge
+        self._merge = merge_fn or (lambda s, i, k: _cuda_merge(s, i, k, sorted_unique=True))
         n_local = 1 if self.distributed else self.world
         self.shards = [index_factory() for _ in range(n_local)]
         self._offsets: Optional[list[int]] = None

@@ -105,9 +105,15 @@ int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_
 /* ---- cross-shard merge ---------------------------------------------------------------------
  * merge_retrieval_results_by_score (DRT/model/utils.py:215-229): union of G per-shard result
  * lists per query (first occurrence of an id wins), sort by score desc (ties: id asc), keep
- * k_out.  Inputs are device arrays laid out [G][nq][k_in]; entries with id < 0 are padding. */
+ * k_out.  Inputs are device arrays laid out [G][nq][k_in]; entries with id < 0 are padding.
+ * flags = DRT_MERGE_SORTED_UNIQUE promises that every list is already ordered (score desc,
+ * id asc, padding last) and that no id occurs in two lists (row-sharded stores): the merge then
+ * ranks entries by binary search instead of sorting. */
+#define DRT_MERGE_DEFAULT        0u
+#define DRT_MERGE_SORTED_UNIQUE  1u
 int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t nq, int k_in,
-                   int k_out, float* out_scores, int64_t* out_ids, int device, void* stream);
+                   int k_out, float* out_scores, int64_t* out_ids, uint32_t flags, int device,
+                   void* stream);
 
 /* ---- in-batch-negative loss ----------------------------------------------------------------
  * SimpleContrastiveLoss.forward (DRT/trainer/losses.py:11-17) and the loss block of

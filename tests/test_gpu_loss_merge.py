@@ -119,6 +119,36 @@ def test_merge_kernel_random_with_padding_and_duplicates():
             np.testing.assert_allclose(D.cpu().numpy()[:, :10], Do[:, :10])
 
 
+def test_sorted_unique_merge_equals_generic_merge():
+    """Rank-based merge (ordered, id-disjoint shard lists) == sort-based merge == oracle."""
+    from denseretrievaltoolkits_b200.store import _cuda_merge
+
+    rng = np.random.default_rng(13)
+    for G, Q, k_in, k_out in [(8, 40, 100, 100), (2, 9, 1000, 1000), (4, 5, 7, 28), (3, 6, 200, 50), (8, 3, 1000, 1000)]:
+        scores = np.sort(np.round(rng.standard_normal((G, Q, k_in)), 1).astype(np.float32), axis=2)[:, :, ::-1].copy()
+        ids = np.empty((G, Q, k_in), np.int64)
+        for g in range(G):                                  # disjoint ascending id ranges; ties -> id asc
+            for q in range(Q):
+                raw = np.sort(rng.choice(10000, size=k_in, replace=False)) + g * 10000
+                order = np.lexsort((raw, -scores[g, q]))    # keep canonical order inside equal scores
+                ids[g, q] = raw
+                scores[g, q] = scores[g, q][order]
+        npad = rng.integers(0, max(1, k_in // 3), size=(G, Q))
+        for g in range(G):
+            for q in range(Q):
+                if npad[g, q]:
+                    ids[g, q, -npad[g, q]:] = -1
+                    scores[g, q, -npad[g, q]:] = np.float32(-3.4028234663852886e38)
+        sc, idt = torch.from_numpy(scores).cuda(), torch.from_numpy(ids).cuda()
+        Df, If = _cuda_merge(sc, idt, k_out, sorted_unique=True)
+        Do, Io = omerge.merge_topk(scores, ids, k_out)
+        np.testing.assert_array_equal(If.cpu().numpy(), Io)
+        np.testing.assert_array_equal(Df.cpu().numpy(), Do)
+        if G * k_in <= 8192:
+            Dg, Ig = _cuda_merge(sc, idt, k_out)
+            assert torch.equal(Ig, If) and torch.equal(Dg, Df)
+
+
 def test_mining_filter_matches_reference_loop():
     from denseretrievaltoolkits_b200.mining import filter_negatives
 
