@@ -150,6 +150,11 @@ def run_reference(args):
     if rank != 0:
         return 0
     cfg = HEADLINE
+    # all host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers)
+    try:
+        torch.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
     ns, qs = 1 << 20, 256
     g = torch.Generator().manual_seed(1234)

@@ -654,50 +654,100 @@ std::mutex g_ce_mu;
 std::map<int, CeWorkspace> g_ce_ws;
 }  // namespace
 
+extern "C++" {
+namespace {
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// cached per-device capability check: the CE entry points are latency sensitive
+int check_device_cached(int device) {
+    static int ok[64] = {0};
+    if (device >= 0 && device < 64 && ok[device]) return DRT_OK;
+    const int rc = check_device(device);
+    if (rc == DRT_OK && device >= 0 && device < 64) ok[device] = 1;
+    return rc;
+}
+
+template <class Cfg>
+void launch_sgemm(const drt::GemmOperand& A, const drt::GemmOperand& Bm, long long M, long long N, long long K,
+                  float* C, cudaStream_t st) {
+    const int vecA = aligned16(A.p) && ((A.s_k == 1 ? A.s_outer : A.s_k) % 4 == 0);
+    const int vecB = aligned16(Bm.p) && ((Bm.s_k == 1 ? Bm.s_outer : Bm.s_k) % 4 == 0);
+    dim3 grid((unsigned)((N + Cfg::BN - 1) / Cfg::BN), (unsigned)((M + Cfg::BM - 1) / Cfg::BM));
+    drt::sgemm_kernel<Cfg><<<grid, Cfg::THREADS, 0, st>>>(A, Bm, M, N, K, C, vecA, vecB);
+}
+inline bool use_large_tiles(long long M, long long N, int sm_count) {
+    return ((M + 63) / 64) * ((N + 63) / 64) >= 2ll * sm_count;
+}
+}  // namespace
+}  // extern "C++"
+
 int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int dim, const int64_t* target,
                        float loss_scale, float* logits_out, float* lse_out, float* loss_rows, float* loss_out,
                        int device, void* stream) {
     if (B <= 0 || P <= 0 || dim <= 0) return fail(DRT_E_INVALID, "bad shape B=%lld P=%lld d=%d", (long long)B, (long long)P, dim);
-    if (dim % 32 != 0) return fail(DRT_E_UNSUPPORTED, "dim %d is not a multiple of 32", dim);
     if (!x || !y || !lse_out || !loss_rows || !loss_out) return fail(DRT_E_INVALID, "NULL pointer");
     if (!target && P / B == 0) return fail(DRT_E_INVALID, "default targets need P >= B");
-    int rc = check_device(device);
+    int rc = check_device_cached(device);
     if (rc != DRT_OK) return rc;
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lk(g_ce_mu);
     CeWorkspace& w = g_ce_ws[device];
-    const int ncol = (int)((P + drt::kCeTN - 1) / drt::kCeTN), nrow = (int)((B + drt::kCeTM - 1) / drt::kCeTM);
+    const bool large = use_large_tiles(B, P, 148);
+    const int bm = large ? drt::GemmLarge::BM : drt::GemmSmall::BM, bn = large ? drt::GemmLarge::BN : drt::GemmSmall::BN;
+    const int ncol = (int)((P + bn - 1) / bn), nrow = (int)((B + bm - 1) / bm);
     if ((rc = w.part_max.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
     if ((rc = w.part_sum.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
     if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
     if ((rc = w.ticket.ensure(64)) != DRT_OK) return rc;
     if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, 64, st)); w.ticket_init = true; }
-    CUDA_TRY(cudaMemsetAsync(w.tgt.p, 0xFF, (size_t)B * 4, st));   // NaN: an out-of-range target poisons the loss
-    drt::inbatch_ce_fwd_kernel<<<dim3(ncol, nrow), drt::kCeThreads, 0, st>>>(
-        x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), loss_scale, logits_out,
-        (float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows, loss_out);
+    const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
+    if (large)
+        drt::inbatch_ce_fwd_kernel<drt::GemmLarge><<<dim3(ncol, nrow), drt::GemmLarge::THREADS, 0, st>>>(
+            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), loss_scale, logits_out,
+            (float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows,
+            loss_out, vec_ok);
+    else
+        drt::inbatch_ce_fwd_kernel<drt::GemmSmall><<<dim3(ncol, nrow), drt::GemmSmall::THREADS, 0, st>>>(
+            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), loss_scale, logits_out,
+            (float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows,
+            loss_out, vec_ok);
     CUDA_TRY(cudaGetLastError());
     return DRT_OK;
 }
 
 int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim, const int64_t* target,
-                       const float* lse, const float* grad_rows, float* work, float* dx, float* dy, int device,
-                       void* stream) {
+                       const float* lse, const float* grad_rows, int grad_stride, float grad_scale, float* work,
+                       float* dx, float* dy, int device, void* stream) {
     if (B <= 0 || P <= 0 || dim <= 0) return fail(DRT_E_INVALID, "bad shape");
-    if (dim % 32 != 0) return fail(DRT_E_UNSUPPORTED, "dim %d is not a multiple of 32", dim);
     if (!x || !y || !lse || !grad_rows || !work) return fail(DRT_E_INVALID, "NULL pointer");
-    int rc = check_device(device);
+    if (grad_stride != 0 && grad_stride != 1) return fail(DRT_E_INVALID, "grad_stride must be 0 (scalar) or 1 (per row)");
+    int rc = check_device_cached(device);
     if (rc != DRT_OK) return rc;
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
-    const int ncol = (int)((P + drt::kCeTN - 1) / drt::kCeTN), nrow = (int)((B + drt::kCeTM - 1) / drt::kCeTM);
-    drt::inbatch_ce_dlogits_kernel<<<dim3(ncol, nrow), drt::kCeThreads, 0, st>>>(
-        x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), lse, grad_rows, work);
-    if (dx) drt::sgemm_strided_kernel<<<dim3((dim + 63) / 64, (unsigned)((B + 63) / 64)), 256, 0, st>>>(
-        work, (long long)P, 1ll, y, (long long)B, (long long)dim, (long long)P, dx);
-    if (dy) drt::sgemm_strided_kernel<<<dim3((dim + 63) / 64, (unsigned)((P + 63) / 64)), 256, 0, st>>>(
-        work, 1ll, (long long)P, x, (long long)P, (long long)dim, (long long)B, dy);
+    const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
+    if (use_large_tiles(B, P, 148)) {
+        using C = drt::GemmLarge;
+        drt::inbatch_ce_dlogits_kernel<C><<<dim3((unsigned)((P + C::BN - 1) / C::BN), (unsigned)((B + C::BM - 1) / C::BM)), C::THREADS, 0, st>>>(
+            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), lse, grad_rows, grad_stride, grad_scale, work, vec_ok);
+    } else {
+        using C = drt::GemmSmall;
+        drt::inbatch_ce_dlogits_kernel<C><<<dim3((unsigned)((P + C::BN - 1) / C::BN), (unsigned)((B + C::BM - 1) / C::BM)), C::THREADS, 0, st>>>(
+            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), lse, grad_rows, grad_stride, grad_scale, work, vec_ok);
+    }
+    // dx[B,d] = dlogits[B,P] · y[P,d]   (A k-contiguous, B n-contiguous)
+    if (dx) {
+        const drt::GemmOperand A{work, (long long)P, 1}, Bm{y, 1, (long long)dim};
+        if (use_large_tiles(B, dim, 148)) launch_sgemm<drt::GemmLarge>(A, Bm, B, dim, P, dx, st);
+        else launch_sgemm<drt::GemmSmall>(A, Bm, B, dim, P, dx, st);
+    }
+    // dy[P,d] = dlogitsᵀ[P,B] · x[B,d]  (A m-contiguous, B n-contiguous)
+    if (dy) {
+        const drt::GemmOperand A{work, 1, (long long)P}, Bm{x, 1, (long long)dim};
+        if (use_large_tiles(P, dim, 148)) launch_sgemm<drt::GemmLarge>(A, Bm, P, dim, B, dy, st);
+        else launch_sgemm<drt::GemmSmall>(A, Bm, P, dim, B, dy, st);
+    }
     CUDA_TRY(cudaGetLastError());
     return DRT_OK;
 }

@@ -5,126 +5,232 @@
 // (DRT/model/biencoder.py:107-116), plus their autograd.
 //
 // The reference computes this in fp32 (TF32 is off by default for torch.matmul), and the loss
-// must match to 1e-4 relative, so the contraction runs as fp32 FFMA (a bf16 tensor-core pass
-// would put ~5e-4 relative error on the loss).  At the named shape (128 x 1024 x 768,
+// must match to 1e-4 relative, so the contraction runs as fp32 FFMA (a single bf16 tensor-core
+// pass would put ~5e-4 relative error on the loss).  At the named shape (128 x 1024 x 768,
 // 0.2 GFLOP, 3.5 MB of operands) the step is launch-latency bound, not FLOP bound; the win
 // over the eager path is one launch for scores + log-sum-exp + NLL (and no HBM round trip of
-// the score matrix unless the caller asks for it), and two launches for the backward.
+// the score matrix unless the caller asks for it), and three launches for the backward.
+//
+// One register-tiled SIMT GEMM core serves all three contractions:
+//   NT  logits  = x · yᵀ          A(m,k)=x[m*d+k]    B(k,n)=y[n*d+k]
+//   NN  dx      = dlogits · y      A(m,k)=dL[m*P+k]   B(k,n)=y[k*d+n]
+//   TN  dy      = dlogitsᵀ · x     A(m,k)=dL[k*P+m]   B(k,n)=x[k*d+n]
+// with two tile shapes: 32x32 / 128 threads (small problems: enough CTAs to cover 148 SMs) and
+// 64x64 / 256 threads (large problems: 2x less L2 traffic per FLOP).
 #pragma once
 #include <cfloat>
 #include <cstdint>
 
 namespace drt {
 
-constexpr int kCeTM = 32;    // logits tile rows  (queries)
-constexpr int kCeTN = 32;    // logits tile cols  (passages)
-constexpr int kCeTK = 32;    // k-step
-constexpr int kCeThreads = 256;
+constexpr int kGemmBK = 16;
 
-// C tile [32x32] = X[m0:m0+32, :] · Y[n0:n0+32, :]^T, fp32.  Thread t computes a 1x4 strip:
-// row = t / 8, cols = 4*(t % 8) .. +3.  Results returned in acc[4].
-__device__ __forceinline__ void ce_tile_logits(const float* __restrict__ x, const float* __restrict__ y,
-                                               long long B, long long P, int dim, long long m0,
-                                               long long n0, float (&sx)[kCeTK][kCeTM + 1],
-                                               float (&sy)[kCeTK][kCeTN + 1], float (&acc)[4]) {
+struct GemmOperand {
+    const float* p;
+    long long s_outer;   // stride of the non-k index (m for A, n for B)
+    long long s_k;       // stride of k
+};
+
+// Tile config: BM x BN outputs, TM x TN per thread, threads = (BM/TM) * (BN/TN)
+template <int BM_, int BN_, int TM_, int TN_>
+struct GemmCfg {
+    static constexpr int BM = BM_, BN = BN_, TM = TM_, TN = TN_;
+    static constexpr int TX = BN / TN, TY = BM / TM, THREADS = TX * TY;
+    static constexpr int PAD = 4;
+};
+using GemmSmall = GemmCfg<32, 32, 4, 2>;    // 128 threads
+using GemmLarge = GemmCfg<64, 64, 4, 4>;    // 256 threads
+
+// One thread moves one float4 of a [ROWS x kGemmBK] operand tile per k-slab (ROWS*kGemmBK/4 ==
+// THREADS).  Element (r, k) lives at p[(r0 + r) * s_outer + (k0 + k) * s_k]; out-of-range -> 0.
+// fetch_vec issues the global load into registers; store_vec writes it into smem laid out
+// [k][row] (row contiguous) -- split so the load latency overlaps the FMAs of the current slab.
+template <int ROWS>
+__device__ __forceinline__ void fetch_vec(float (&v)[4], const GemmOperand& op, long long r0, long long nrows,
+                                          long long k0, long long K, bool vec_ok) {
     const int t = threadIdx.x;
-    const int r = t >> 3, c4 = (t & 7) * 4;
-    acc[0] = acc[1] = acc[2] = acc[3] = 0.f;
-    // loader mapping: 256 threads load 32 rows x 32 k of X and of Y (one float4 each)
-    const int lr = t >> 3, lk = (t & 7) * 4;
-    for (int k0 = 0; k0 < dim; k0 += kCeTK) {
-        float4 vx = make_float4(0.f, 0.f, 0.f, 0.f), vy = vx;
-        if (m0 + lr < B) vx = *reinterpret_cast<const float4*>(x + (m0 + lr) * dim + k0 + lk);
-        if (n0 + lr < P) vy = *reinterpret_cast<const float4*>(y + (n0 + lr) * dim + k0 + lk);
-        __syncthreads();
-        sx[lk + 0][lr] = vx.x; sx[lk + 1][lr] = vx.y; sx[lk + 2][lr] = vx.z; sx[lk + 3][lr] = vx.w;
-        sy[lk + 0][lr] = vy.x; sy[lk + 1][lr] = vy.y; sy[lk + 2][lr] = vy.z; sy[lk + 3][lr] = vy.w;
-        __syncthreads();
+    v[0] = v[1] = v[2] = v[3] = 0.f;
+    if (op.s_k == 1) {            // k contiguous: 4 consecutive k of one row
+        constexpr int VEC_PER_ROW = kGemmBK / 4;
+        const int r = t / VEC_PER_ROW, kk = (t % VEC_PER_ROW) * 4;
+        const long long gr = r0 + r, gk = k0 + kk;
+        if (gr < nrows) {
+            const float* src = op.p + gr * op.s_outer + gk;
+            if (vec_ok && gk + 3 < K) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
 #pragma unroll
-        for (int kk = 0; kk < kCeTK; ++kk) {
-            const float a = sx[kk][r];
-            acc[0] = fmaf(a, sy[kk][c4 + 0], acc[0]);
-            acc[1] = fmaf(a, sy[kk][c4 + 1], acc[1]);
-            acc[2] = fmaf(a, sy[kk][c4 + 2], acc[2]);
-            acc[3] = fmaf(a, sy[kk][c4 + 3], acc[3]);
+                for (int j = 0; j < 4; ++j) if (gk + j < K) v[j] = src[j];
+            }
+        }
+    } else {                      // row index contiguous: 4 consecutive rows of one k
+        constexpr int VEC_PER_K = ROWS / 4;
+        const int kk = t / VEC_PER_K, r = (t % VEC_PER_K) * 4;
+        const long long gr = r0 + r, gk = k0 + kk;
+        if (gk < K) {
+            const float* src = op.p + gk * op.s_k + gr;
+            if (vec_ok && gr + 3 < nrows) {
+                const float4 q = __ldg(reinterpret_cast<const float4*>(src));
+                v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) if (gr + j < nrows) v[j] = src[j];
+            }
         }
     }
 }
+template <int ROWS, int LD>
+__device__ __forceinline__ void store_vec(float (*dst)[LD], const float (&v)[4], bool k_contiguous) {
+    const int t = threadIdx.x;
+    if (k_contiguous) {
+        constexpr int VEC_PER_ROW = kGemmBK / 4;
+        const int r = t / VEC_PER_ROW, kk = (t % VEC_PER_ROW) * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dst[kk + j][r] = v[j];
+    } else {
+        constexpr int VEC_PER_K = ROWS / 4;
+        const int kk = t / VEC_PER_K, r = (t % VEC_PER_K) * 4;
+        *reinterpret_cast<float4*>(&dst[kk][r]) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+}
 
-// Forward: grid (ceil(P/32), ceil(B/32)).  Each CTA produces per-row partial (max, sum-exp) over
-// its 32 columns; the last CTA to finish (atomic ticket) folds the partials into lse / per-row
+// acc[TM][TN] = tile (m0.., n0..) of sum_k A(m,k) B(k,n).  Thread (ty, tx) owns rows
+// m0 + ty*TM .. and columns n0 + tx*TN ..; lanes of a warp vary tx fastest, so the A fragment is
+// a smem broadcast and the B fragment one contiguous wavefront.
+template <class Cfg>
+__device__ __forceinline__ void gemm_tile(const GemmOperand& A, const GemmOperand& B, long long M, long long N,
+                                          long long K, long long m0, long long n0, bool vecA, bool vecB,
+                                          float (&acc)[Cfg::TM][Cfg::TN]) {
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, TM = Cfg::TM, TN = Cfg::TN;
+    static_assert(BM * kGemmBK / 4 == Cfg::THREADS && BN * kGemmBK / 4 == Cfg::THREADS, "one float4 per thread per slab");
+    __shared__ __align__(16) float sa[2][kGemmBK][BM + Cfg::PAD];
+    __shared__ __align__(16) float sb[2][kGemmBK][BN + Cfg::PAD];
+    const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
+    const bool a_kc = A.s_k == 1, b_kc = B.s_k == 1;
+#pragma unroll
+    for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+    float ra[4], rb[4];
+    fetch_vec<BM>(ra, A, m0, M, 0, K, vecA);
+    fetch_vec<BN>(rb, B, n0, N, 0, K, vecB);
+    store_vec<BM>(sa[0], ra, a_kc);
+    store_vec<BN>(sb[0], rb, b_kc);
+    __syncthreads();
+    int buf = 0;
+    for (long long k0 = 0; k0 < K; k0 += kGemmBK) {
+        const bool more = k0 + kGemmBK < K;
+        if (more) {               // global loads of the next slab fly while this slab is multiplied
+            fetch_vec<BM>(ra, A, m0, M, k0 + kGemmBK, K, vecA);
+            fetch_vec<BN>(rb, B, n0, N, k0 + kGemmBK, K, vecB);
+        }
+#pragma unroll
+        for (int kk = 0; kk < kGemmBK; ++kk) {
+            float a[TM], b[TN];
+            const float4 a4 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * TM]);
+            a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
+            if constexpr (TN == 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * TN]);
+                b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+            } else {
+                const float2 b2 = *reinterpret_cast<const float2*>(&sb[buf][kk][tx * TN]);
+                b[0] = b2.x; b[1] = b2.y;
+            }
+#pragma unroll
+            for (int i = 0; i < TM; ++i)
+#pragma unroll
+                for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        if (more) {
+            store_vec<BM>(sa[buf ^ 1], ra, a_kc);
+            store_vec<BN>(sb[buf ^ 1], rb, b_kc);
+        }
+        __syncthreads();
+        buf ^= 1;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Forward: grid (ceil(P/BN), ceil(B/BM)).  Each CTA produces per-row partial (max, sum-exp) over
+// its BN columns; the last CTA to finish (atomic ticket) folds the partials into lse / per-row
 // loss / the scaled total in a fixed order, so the result is deterministic.
-__global__ void __launch_bounds__(kCeThreads)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS)
 inbatch_ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, long long B,
                       long long P, int dim, const long long* __restrict__ target,
                       long long target_stride, float loss_scale, float* logits_out,
                       float* part_max, float* part_sum, float* tgt_logit, unsigned int* ticket,
-                      float* lse_out, float* loss_rows, float* loss_out) {
-    __shared__ float sx[kCeTK][kCeTM + 1];
-    __shared__ float sy[kCeTK][kCeTN + 1];
+                      float* lse_out, float* loss_rows, float* loss_out, int vec_ok) {
+    constexpr int TM = Cfg::TM, TN = Cfg::TN;
     __shared__ bool s_last;
-    const long long m0 = static_cast<long long>(blockIdx.y) * kCeTM;
-    const long long n0 = static_cast<long long>(blockIdx.x) * kCeTN;
-    float acc[4];
-    ce_tile_logits(x, y, B, P, dim, m0, n0, sx, sy, acc);
+    const long long m0 = static_cast<long long>(blockIdx.y) * Cfg::BM;
+    const long long n0 = static_cast<long long>(blockIdx.x) * Cfg::BN;
+    float acc[TM][TN];
+    gemm_tile<Cfg>(GemmOperand{x, dim, 1}, GemmOperand{y, dim, 1}, B, P, dim, m0, n0, vec_ok, vec_ok, acc);
 
-    const int t = threadIdx.x, r = t >> 3, c4 = (t & 7) * 4;
-    const long long row = m0 + r;
-    const long long tcol = (row < B) ? (target ? target[row] : row * target_stride) : -1;
-    float mx = -FLT_MAX;
+    const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const long long col = n0 + c4 + j;
-        if (row < B && col < P) {
-            if (logits_out) logits_out[row * P + col] = acc[j];
-            if (col == tcol) tgt_logit[row] = acc[j];
-            mx = fmaxf(mx, acc[j]);
+    for (int i = 0; i < TM; ++i) {
+        const long long row = m0 + ty * TM + i;
+        const long long tcol = (row < B) ? (target ? target[row] : row * target_stride) : -1;
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const long long col = n0 + tx * TN + j;
+            if (row < B && col < P) {
+                if (logits_out) logits_out[row * P + col] = acc[i][j];
+                if (col == tcol) tgt_logit[row] = acc[i][j];
+                mx = fmaxf(mx, acc[i][j]);
+            }
         }
-    }
-    // reduce over the 8 threads that share a row (consecutive lanes)
+        // the TX threads sharing this row are consecutive lanes (TX = 16 divides the warp)
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float se = 0.f;
+        for (int o = Cfg::TX / 2; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float se = 0.f;
 #pragma unroll
-    for (int j = 0; j < 4; ++j)
-        if (row < B && n0 + c4 + j < P) se += expf(acc[j] - mx);
+        for (int j = 0; j < TN; ++j)
+            if (row < B && n0 + tx * TN + j < P) se += expf(acc[i][j] - mx);
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
-    if ((t & 7) == 0 && row < B) {
-        part_max[row * gridDim.x + blockIdx.x] = mx;
-        part_sum[row * gridDim.x + blockIdx.x] = se;
+        for (int o = Cfg::TX / 2; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
+        if (tx == 0 && row < B) {
+            part_max[row * gridDim.x + blockIdx.x] = mx;
+            part_sum[row * gridDim.x + blockIdx.x] = se;
+        }
     }
     // ---- last-CTA reduction ----
     __threadfence();
     __syncthreads();
-    if (t == 0) {
+    if (threadIdx.x == 0) {
         const unsigned int total = gridDim.x * gridDim.y;
         s_last = (atomicAdd(ticket, 1u) == total - 1u);
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    __shared__ double s_red[kCeThreads];
+    __shared__ double s_red[Cfg::THREADS];
     double local = 0.0;
     const int ncol = gridDim.x;
-    for (long long i = t; i < B; i += kCeThreads) {
+    for (long long i = threadIdx.x; i < B; i += Cfg::THREADS) {
         float m = -FLT_MAX;
         for (int c = 0; c < ncol; ++c) m = fmaxf(m, __ldcg(part_max + i * ncol + c));
         float s = 0.f;
         for (int c = 0; c < ncol; ++c) s += __ldcg(part_sum + i * ncol + c) * expf(__ldcg(part_max + i * ncol + c) - m);
         const float lse = m + logf(s);
-        const float li = lse - __ldcg(tgt_logit + i);
+        const long long tc = target ? target[i] : i * target_stride;
+        // an out-of-range target poisons the loss instead of reading a stale logit
+        const float li = (tc >= 0 && tc < P) ? lse - __ldcg(tgt_logit + i) : __int_as_float(0x7fc00000);
         lse_out[i] = lse;
         loss_rows[i] = li;
         local += static_cast<double>(li);
     }
-    s_red[t] = local;
+    s_red[threadIdx.x] = local;
     __syncthreads();
-    for (int o = kCeThreads / 2; o > 0; o >>= 1) {
-        if (t < o) s_red[t] += s_red[t + o];
+    for (int o = Cfg::THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
         __syncthreads();
     }
-    if (t == 0) {
+    if (threadIdx.x == 0) {
         *loss_out = static_cast<float>(s_red[0] * static_cast<double>(loss_scale));
         *ticket = 0u;    // re-arm for the next launch on this stream
     }
@@ -132,74 +238,49 @@ inbatch_ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, 
 
 // Backward step 1: dlogits[i,j] = g_i * (exp(logit_ij - lse_i) - [j == target_i]); logits are
 // recomputed tile by tile (they were never stored).
-__global__ void __launch_bounds__(kCeThreads)
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS)
 inbatch_ce_dlogits_kernel(const float* __restrict__ x, const float* __restrict__ y, long long B,
                           long long P, int dim, const long long* __restrict__ target,
                           long long target_stride, const float* __restrict__ lse,
-                          const float* __restrict__ grad_rows, float* __restrict__ dlogits) {
-    __shared__ float sx[kCeTK][kCeTM + 1];
-    __shared__ float sy[kCeTK][kCeTN + 1];
-    const long long m0 = static_cast<long long>(blockIdx.y) * kCeTM;
-    const long long n0 = static_cast<long long>(blockIdx.x) * kCeTN;
-    float acc[4];
-    ce_tile_logits(x, y, B, P, dim, m0, n0, sx, sy, acc);
-    const int t = threadIdx.x, r = t >> 3, c4 = (t & 7) * 4;
-    const long long row = m0 + r;
-    if (row >= B) return;
-    const long long tcol = target ? target[row] : row * target_stride;
-    const float l = lse[row], g = grad_rows[row];
+                          const float* __restrict__ grad_rows, int grad_stride, float grad_scale,
+                          float* __restrict__ dlogits, int vec_ok) {
+    constexpr int TM = Cfg::TM, TN = Cfg::TN;
+    const long long m0 = static_cast<long long>(blockIdx.y) * Cfg::BM;
+    const long long n0 = static_cast<long long>(blockIdx.x) * Cfg::BN;
+    float acc[TM][TN];
+    gemm_tile<Cfg>(GemmOperand{x, dim, 1}, GemmOperand{y, dim, 1}, B, P, dim, m0, n0, vec_ok, vec_ok, acc);
+    const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const long long col = n0 + c4 + j;
-        if (col < P) dlogits[row * P + col] = g * (expf(acc[j] - l) - (col == tcol ? 1.f : 0.f));
+    for (int i = 0; i < TM; ++i) {
+        const long long row = m0 + ty * TM + i;
+        if (row >= B) continue;
+        const long long tcol = target ? target[row] : row * target_stride;
+        const float l = lse[row], g = grad_scale * grad_rows[row * grad_stride];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const long long col = n0 + tx * TN + j;
+            if (col < P) dlogits[row * P + col] = g * (expf(acc[i][j] - l) - (col == tcol ? 1.f : 0.f));
+        }
     }
 }
 
-// Backward step 2: generic fp32 C[M,N] = sum_k A(m,k) * Bm[k,N] with A(m,k) = A[m*sam + k*sak].
-//   dx = dlogits · y      : A = dlogits (sam = P, sak = 1), Bm = y, M = B, K = P
-//   dy = dlogitsᵀ · x     : A = dlogits (sam = 1, sak = P), Bm = x, M = P, K = B
-// 64x64 tiles, 256 threads, 4x4 outputs per thread.
-__global__ void __launch_bounds__(256)
-sgemm_strided_kernel(const float* __restrict__ A, long long sam, long long sak,
-                     const float* __restrict__ Bm, long long M, long long N, long long K,
-                     float* __restrict__ C) {
-    __shared__ float sa[16][64 + 1];
-    __shared__ float sb[16][64 + 4];
-    const int t = threadIdx.x;
-    const long long m0 = static_cast<long long>(blockIdx.y) * 64, n0 = static_cast<long long>(blockIdx.x) * 64;
-    const int tr = (t >> 4) * 4, tc = (t & 15) * 4;
-    float acc[4][4] = {};
-    for (long long k0 = 0; k0 < K; k0 += 16) {
-        __syncthreads();
-        // A tile: 64 rows x 16 k.  Pick the loader orientation that is contiguous in memory.
-        for (int i = t; i < 64 * 16; i += 256) {
-            int mm, kk;
-            if (sak == 1) { mm = i >> 4; kk = i & 15; } else { kk = i >> 6; mm = i & 63; }
-            const long long m = m0 + mm, k = k0 + kk;
-            sa[kk][mm] = (m < M && k < K) ? A[m * sam + k * sak] : 0.f;
-        }
-        for (int i = t; i < 16 * 64; i += 256) {
-            const int kk = i >> 6, nn = i & 63;
-            const long long k = k0 + kk, n = n0 + nn;
-            sb[kk][nn] = (k < K && n < N) ? Bm[k * N + n] : 0.f;
-        }
-        __syncthreads();
+// Backward step 2: C[M,N] = sum_k A(m,k) B(k,n) with arbitrary operand strides (see header).
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS)
+sgemm_kernel(GemmOperand A, GemmOperand Bm, long long M, long long N, long long K, float* __restrict__ C,
+             int vecA, int vecB) {
+    constexpr int TM = Cfg::TM, TN = Cfg::TN;
+    const long long m0 = static_cast<long long>(blockIdx.y) * Cfg::BM;
+    const long long n0 = static_cast<long long>(blockIdx.x) * Cfg::BN;
+    float acc[TM][TN];
+    gemm_tile<Cfg>(A, Bm, M, N, K, m0, n0, vecA, vecB, acc);
+    const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
-        for (int kk = 0; kk < 16; ++kk) {
-            float a[4], b[4];
+    for (int i = 0; i < TM; ++i)
 #pragma unroll
-            for (int i = 0; i < 4; ++i) { a[i] = sa[kk][tr + i]; b[i] = sb[kk][tc + i]; }
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-        }
-    }
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const long long m = m0 + tr + i, n = n0 + tc + j;
+        for (int j = 0; j < TN; ++j) {
+            const long long m = m0 + ty * TM + i, n = n0 + tx * TN + j;
             if (m < M && n < N) C[m * N + n] = acc[i][j];
         }
 }

@@ -2,8 +2,8 @@
 
 `SimpleContrastiveLoss.forward(x, y, target=None, reduction='mean')` (losses.py:11-17) and
 `DistributedContrastiveLoss` (losses.py:20-40) keep their names, arguments and values; the
-score matrix, log-sum-exp and NLL run as one CUDA launch (`drt_inbatch_ce_fwd`) and the
-backward as `drt_inbatch_ce_bwd`, both fp32 like the reference's `torch.matmul`.
+score matrix, log-sum-exp, NLL and the reduction run as ONE CUDA launch (`drt_inbatch_ce_fwd`)
+and the backward as three (`drt_inbatch_ce_bwd`), all fp32 like the reference's `torch.matmul`.
 `inbatch_scores_and_loss` serves the loss block of `DRModel.forward`
 (DRT/model/biencoder.py:107-119), which also returns the score matrix (biencoder.py:122).
 
@@ -17,86 +17,91 @@ from torch import distributed as dist
 
 from . import _lib
 
+_REDUCTIONS = ("mean", "sum", "none")
 
-def _check_inputs(x: Tensor, y: Tensor) -> None:
-    if not (x.is_cuda and y.is_cuda):
-        raise RuntimeError("denseretrievaltoolkits_b200 losses need CUDA tensors: there is no CPU fallback")
-    if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
-        raise RuntimeError(f"expected x [B,d] and y [P,d], got {tuple(x.shape)} and {tuple(y.shape)}")
+
+def _f32c(t: Tensor) -> Tensor:
+    t = t.detach()
+    if t.dtype is not torch.float32:
+        t = t.to(torch.float32)
+    return t if t.is_contiguous() else t.contiguous()
 
 
 class _InBatchCE(torch.autograd.Function):
-    """Returns (per-row loss [B], logits [B,P] or empty)."""
+    """(x [B,d], y [P,d], target|None, reduction, want_logits) -> (loss, logits|empty).
+    `loss` is a 0-dim tensor for 'mean'/'sum' and [B] for 'none'."""
 
     @staticmethod
-    def forward(ctx, x: Tensor, y: Tensor, target, want_logits: bool):
-        _check_inputs(x, y)
+    def forward(ctx, x: Tensor, y: Tensor, target, reduction: str, want_logits: bool):
+        if not (x.is_cuda and y.is_cuda):
+            raise RuntimeError("denseretrievaltoolkits_b200 losses need CUDA tensors: there is no CPU fallback")
+        if x.dim() != 2 or y.dim() != 2 or x.shape[1] != y.shape[1]:
+            raise RuntimeError(f"expected x [B,d] and y [P,d], got {tuple(x.shape)} and {tuple(y.shape)}")
+        if reduction not in _REDUCTIONS:
+            raise ValueError(f"{reduction} is not a valid value for reduction")
         lib = _lib.load()
-        xc = x.detach().to(torch.float32).contiguous()
-        yc = y.detach().to(torch.float32).contiguous()
+        xc, yc = _f32c(x), _f32c(y)
         B, d = xc.shape
         P = yc.shape[0]
         dev = xc.device
         tgt = None
         if target is not None:
-            tgt = target.detach().to(device=dev, dtype=torch.int64).contiguous()
+            tgt = target.detach()
+            if tgt.dtype is not torch.int64 or tgt.device != dev or not tgt.is_contiguous():
+                tgt = tgt.to(device=dev, dtype=torch.int64).contiguous()
         logits = torch.empty((B, P), dtype=torch.float32, device=dev) if want_logits else None
-        lse = torch.empty((B,), dtype=torch.float32, device=dev)
-        rows = torch.empty((B,), dtype=torch.float32, device=dev)
-        total = torch.empty((1,), dtype=torch.float32, device=dev)
+        lse = torch.empty((B,), dtype=torch.float32, device=dev)           # saved for backward
+        out = torch.empty((B + 1,), dtype=torch.float32, device=dev)       # per-row loss | total
+        scale = 1.0 / B if reduction == "mean" else 1.0
+        stream = _lib.current_stream_ptr(dev.index)
+        base = out.data_ptr()
         _lib.check(lib.drt_inbatch_ce_fwd(
-            xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if tgt is not None else None, 1.0,
-            logits.data_ptr() if logits is not None else None, lse.data_ptr(), rows.data_ptr(),
-            total.data_ptr(), dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_fwd")
-        ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else torch.empty(0, device=dev))
+            xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if tgt is not None else None, scale,
+            logits.data_ptr() if logits is not None else None, lse.data_ptr(), base, base + 4 * B,
+            dev.index, stream), "inbatch_ce_fwd")
+        ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else lse)
         ctx.has_target = tgt is not None
+        ctx.reduction = reduction
+        ctx.scale = scale
         ctx.in_dtypes = (x.dtype, y.dtype)
         if logits is None:
-            logits = torch.empty(0, device=dev)
+            logits = out.new_empty(0)
         ctx.mark_non_differentiable(logits)
-        return rows, logits
+        loss = out[:B] if reduction == "none" else out[B]
+        return loss, logits
 
     @staticmethod
-    def backward(ctx, grad_rows: Tensor, _grad_logits):
+    def backward(ctx, grad_loss: Tensor, _grad_logits):
         xc, yc, lse, tgt = ctx.saved_tensors
         lib = _lib.load()
         B, d = xc.shape
         P = yc.shape[0]
         dev = xc.device
-        g = grad_rows.detach().to(torch.float32).contiguous()
+        g = _f32c(grad_loss)
+        per_row = ctx.reduction == "none"
         work = torch.empty((B, P), dtype=torch.float32, device=dev)
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = torch.empty_like(xc) if need_x else None
         dy = torch.empty_like(yc) if need_y else None
         _lib.check(lib.drt_inbatch_ce_bwd(
             xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if ctx.has_target else None,
-            lse.data_ptr(), g.data_ptr(), work.data_ptr(),
+            lse.data_ptr(), g.data_ptr(), 1 if per_row else 0, ctx.scale, work.data_ptr(),
             dx.data_ptr() if dx is not None else None, dy.data_ptr() if dy is not None else None,
             dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_bwd")
-        if dx is not None:
+        if dx is not None and ctx.in_dtypes[0] is not torch.float32:
             dx = dx.to(ctx.in_dtypes[0])
-        if dy is not None:
+        if dy is not None and ctx.in_dtypes[1] is not torch.float32:
             dy = dy.to(ctx.in_dtypes[1])
-        return dx, dy, None, None
-
-
-def _reduce(rows: Tensor, reduction: str) -> Tensor:
-    if reduction == "mean":
-        return rows.mean()
-    if reduction == "sum":
-        return rows.sum()
-    if reduction == "none":
-        return rows
-    raise ValueError(f"{reduction} is not a valid value for reduction")
+        return dx, dy, None, None, None
 
 
 def inbatch_scores_and_loss(q_reps: Tensor, p_reps: Tensor, n_passages: int, return_scores: bool = True):
     """Loss block of DRModel.forward (biencoder.py:107-116): scores = q·pᵀ,
     target = arange(B) * train_n_passages, mean cross entropy.  Returns (loss, scores|None)."""
     B = q_reps.shape[0]
-    target = torch.arange(B, device=q_reps.device, dtype=torch.long) * int(n_passages)
-    rows, logits = _InBatchCE.apply(q_reps, p_reps, target, bool(return_scores))
-    return rows.mean(), (logits if return_scores else None)
+    target = torch.arange(0, B * int(n_passages), int(n_passages), device=q_reps.device, dtype=torch.long)
+    loss, logits = _InBatchCE.apply(q_reps, p_reps, target, "mean", bool(return_scores))
+    return loss, (logits if return_scores else None)
 
 
 class SimpleContrastiveLoss(nn.Module):
@@ -104,8 +109,7 @@ class SimpleContrastiveLoss(nn.Module):
         super().__init__()
 
     def forward(self, x: Tensor, y: Tensor, target: Tensor = None, reduction: str = "mean"):
-        rows, _ = _InBatchCE.apply(x, y, target, False)
-        return _reduce(rows, reduction)
+        return _InBatchCE.apply(x, y, target, reduction, False)[0]
 
 
 class DistributedContrastiveLoss(SimpleContrastiveLoss):

@@ -129,12 +129,15 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
                        float* logits_out, float* lse_out, float* loss_rows, float* loss_out,
                        int device, void* stream);
 
-/* Backward of the above: dlogits[i,j] = g_i * (softmax(logits)[i,j] - [j == target[i]]), with
- * g_i = grad_rows[i] (device float[B]); dx = dlogits·y, dy = dlogitsᵀ·x.  `work` is a device
- * scratch of B*P floats (holds dlogits). dx / dy may be NULL to skip that gradient. */
+/* Backward of the above: dlogits[i,j] = g_i * (softmax(logits)[i,j] - [j == target[i]]) with
+ * g_i = grad_scale * grad_rows[i * grad_stride]: grad_stride = 1 for a per-row upstream gradient
+ * (reduction='none'), 0 when grad_rows points at ONE device float (reduction='mean'/'sum': the
+ * scalar upstream gradient, grad_scale = 1/B or 1).  dx = dlogits·y, dy = dlogitsᵀ·x.  `work` is
+ * a device scratch of B*P floats (holds dlogits).  dx / dy may be NULL to skip that gradient. */
 int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim,
                        const int64_t* target, const float* lse, const float* grad_rows,
-                       float* work, float* dx, float* dy, int device, void* stream);
+                       int grad_stride, float grad_scale, float* work, float* dx, float* dy,
+                       int device, void* stream);
 
 /* ---- mining filter -------------------------------------------------------------------------
  * process_sample (DRT/trainer/sampler.py:69-80): walk each query's retrieved ids in rank order,
