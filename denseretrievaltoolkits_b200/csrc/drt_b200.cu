@@ -277,6 +277,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     CUtensorMap tmap_d;
     int tmap_seg = -1;
     size_t n_timed = 0;
+    bool frozen = false;
     for (const Chunk& c : chunks) {
         const int64_t seg_valid = std::min<int64_t>(s->seg_rows, s->ntotal - (int64_t)c.seg * s->seg_rows);
         if (c.seg != tmap_seg) {
@@ -313,8 +314,18 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                           : launch_filter<1>(tmap_q, tmap_d, p, s->sm_count, st);
         if (rc != DRT_OK) return rc;
         if (timed) { CUDA_TRY(cudaEventRecord(s->ev[2 * n_timed + 1], st)); ++n_timed; }
-        drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
-        s->stats[0] += 2;
+        // Trim + publish thresholds after the chunk -- unless the thresholds are already so tight
+        // that everything the REST of the corpus is expected to admit (keep * remaining / seen
+        // per query, thresholds frozen) fits the buffer many times over; the last chunk always
+        // trims, because K2 reads at most `keep` candidates.
+        const int64_t seen = (int64_t)c.seg * s->seg_rows + c.row1;
+        const bool last = (&c == &chunks.back());
+        if (!frozen || last) {
+            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
+            s->stats[0] += 1;
+            if (attempt == 0 && (double)keep * (double)(s->ntotal - seen) / (double)seen < (double)(cap - keep) / 8.0) frozen = true;
+        }
+        s->stats[0] += 1;
         s->stats[1] += 1;
     }
     {

@@ -121,22 +121,30 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr,
         for (int j = 1; j < 8; ++j) m = fmaxf(m, __uint_as_float(v[8 * b + j]));
         mb[b] = m;
     }
-    if (fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) > thr) {  // rare once the threshold warmed up
+    const bool any_hit = fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3])) > thr;
+    if (__any_sync(0xffffffffu, any_hit)) {  // warp-uniform; rare once the threshold warmed up
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-            if (mb[b] > thr) {
+            // warp-uniform entry, then branch-free (predicated) staging: every lane's hits of
+            // this sub-block are handled by the same instruction stream, so dense admissions
+            // (the threshold warm-up chunks, large k) do not serialise lane by lane
+            if (__any_sync(0xffffffffu, mb[b] > thr)) {
 #pragma unroll
                 for (int j = 8 * b; j < 8 * b + 8; ++j) {
                     const float f = __uint_as_float(v[j]);
-                    if (f > thr && j < nvalid) {
-                        const uint64_t key = pack_key(f, row_id0 + j);
-                        asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * (kTileM * 8)), "l"(key) : "memory");
-                        if (++scnt == kStageSlots) {
-                            flush_staging(my_stage, kStageSlots, p, q);
-                            scnt = 0;
-                        }
-                    }
+                    const bool hit = (f > thr) && (j < nvalid);
+                    const uint64_t key = pack_key(f, row_id0 + j);
+                    if (hit) asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * (kTileM * 8)), "l"(key) : "memory");
+                    scnt += hit ? 1u : 0u;
                 }
+            }
+            // A sub-block adds at most 8 entries, so keeping every lane at <= 8 staged entries
+            // here bounds the staging at 16.  When one lane runs full the WHOLE warp flushes:
+            // the lanes' atomics (different queries, different addresses) are in flight together
+            // instead of each lane stalling the warp for its own round trip.
+            if (__any_sync(0xffffffffu, scnt > kStageSlots - 8)) {
+                if (scnt) flush_staging(my_stage, scnt, p, q);
+                scnt = 0;
             }
         }
     }

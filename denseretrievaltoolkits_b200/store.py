@@ -129,6 +129,14 @@ class ShardedCorpusStore:
         (D [Q,k], I [Q,k]).  Collective: all ranks must call with equal (Q, k)."""
         if self._offsets is None:
             self.finalize()
+        host_in = isinstance(q, np.ndarray)
+        dev = getattr(self.shards[0], "device", None)
+        if host_in and dev is not None and torch.cuda.is_available():
+            # host queries: one H2D copy, the device path end to end, one D2H copy of the merged
+            # result (instead of bouncing every shard's candidates through host memory)
+            qd = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).cuda(dev, non_blocking=True)
+            Dm, Im = self.search(qd, k)
+            return Dm.cpu().numpy(), Im.cpu().numpy()
         if self.distributed:
             D, I = self.shards[0].search(q, k, id_offset=self._offsets[self.rank])
             as_numpy = isinstance(D, np.ndarray)
