@@ -11,14 +11,15 @@
 // (score,row) in shared memory; staged candidates are appended to the query's list in global
 // memory with one atomicAdd per flush (rare: O(k log N) candidates per query per search).
 //
-// Roles inside a CTA (192 threads):
+// Roles inside a CTA (320 threads):
 //   warp 0    TMA producer: streams 128x64 query k-blocks and 256x64 (128x64 per CTA in pair
 //             mode) corpus k-blocks into a 128B-swizzled smem ring.
 //   warp 1    MMA issuer: one thread issues tcgen05.mma (M=128*kCtas, N=256, K=16) four times per
 //             k-block into one of two 256-column TMEM accumulator stages; tcgen05.commit frees
 //             smem slots and publishes finished accumulators.
-//   warps 2-5 epilogue: one warp per TMEM lane quarter; overlaps with the MMA of the next tile
-//             through the second accumulator stage.
+//   warps 2-9 epilogue: two warps per TMEM lane quarter (each takes 128 of the tile's 256
+//             columns); overlaps with the MMA of the next tile through the second accumulator
+//             stage.
 // kCtas = 2 runs the same protocol on a CTA pair (cta_group::2): each CTA owns 128 queries and
 // loads half of every corpus tile, halving the corpus-operand smem/L2 traffic per FLOP.
 //
@@ -36,7 +37,9 @@ namespace drt {
 constexpr int kTileM = 128;     // queries per CTA
 constexpr int kTileN = 256;     // corpus rows per tile (per CTA pair in pair mode)
 constexpr int kBlockK = 64;     // bf16 elements per k-block = one 128-byte swizzle span
-constexpr int kFilterThreads = 192;
+constexpr int kEpilogueWarps = 8;
+constexpr int kEpilogueThreads = kEpilogueWarps * 32;
+constexpr int kFilterThreads = 64 + kEpilogueThreads;   // TMA warp + MMA warp + epilogue
 constexpr int kStageSlots = 16; // staged candidates per epilogue thread before a flush
 
 struct FilterParams {
@@ -77,7 +80,7 @@ struct FilterCfg {
     static constexpr uint32_t kBBytes = kBRows * kBlockK * 2;             // 32 KB | 16 KB
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr uint32_t kBarBytes = 256;                            // (2*kStages+4) mbarriers + tmem holder
-    static constexpr uint32_t kStagingBytes = kStageSlots * kTileM * 8;   // 16 KB candidate staging
+    static constexpr uint32_t kStagingBytes = kStageSlots * kEpilogueThreads * 8;   // 32 KB candidate staging
     static constexpr uint32_t kSmemBytes = kStages * kStageBytes + kBarBytes + kStagingBytes + 1024;
     static_assert((2 * kStages + 4) * 8 + 8 <= kBarBytes, "barrier block too small");
 };
@@ -95,13 +98,14 @@ __device__ __forceinline__ void tmem_ld_wait_regs(uint32_t (&r)[32]) {
                  : "memory");
 }
 
-// Append this thread's `n` staged candidates (smem slots my_stage + i*1024) to query q's list.
+// Append this thread's `n` staged candidates (smem slots my_stage + i*kSlotStride) to query q's list.
+constexpr uint32_t kSlotStride = kEpilogueThreads * 8;
 __device__ __noinline__ void flush_staging(uint32_t my_stage, uint32_t n, const FilterParams& p, int q) {
     const uint32_t base = atomicAdd(p.cnt + q, n);
     uint64_t* dst = p.cand + static_cast<size_t>(q) * p.cap;
     for (uint32_t i = 0; i < n; ++i) {
         uint64_t key;
-        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(key) : "r"(my_stage + i * (kTileM * 8)));
+        asm volatile("ld.shared.u64 %0, [%1];" : "=l"(key) : "r"(my_stage + i * kSlotStride));
         if (base + i < p.cap) dst[base + i] = key;
     }
 }
@@ -134,7 +138,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr,
                     const float f = __uint_as_float(v[j]);
                     const bool hit = (f > thr) && (j < nvalid);
                     const uint64_t key = pack_key(f, row_id0 + j);
-                    if (hit) asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * (kTileM * 8)), "l"(key) : "memory");
+                    if (hit) asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * kSlotStride), "l"(key) : "memory");
                     scnt += hit ? 1u : 0u;
                 }
             }
@@ -188,7 +192,7 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
         }
         for (int a = 0; a < 2; ++a) {
             ptx::mbar_init(tfull_bar(a), 1);           // one tcgen05.commit
-            ptx::mbar_init(tempty_bar(a), 4 * kCtas);  // one arrive per epilogue warp
+            ptx::mbar_init(tempty_bar(a), kEpilogueWarps * kCtas);  // one arrive per epilogue warp
         }
         ptx::fence_mbar_init();
     }
@@ -278,8 +282,10 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else {
         // ================================ epilogue ====================================
         const uint32_t quarter = warp & 3u;   // TMEM lanes [32*quarter, +32) belong to this warp
+        const uint32_t half = (warp - 2u) >> 2;   // which 128 columns of the tile this warp filters
+        constexpr int kColsPerWarp = kTileN / (kEpilogueWarps / 4);
         const uint32_t lead_tempty0 = (kCtas == 2) ? ptx::mapa(tempty_bar(0), 0) : tempty_bar(0);
-        const uint32_t my_stage = staging + (quarter * 32u + lane) * 8u;
+        const uint32_t my_stage = staging + ((warp - 2u) * 32u + lane) * 8u;
         uint32_t scnt = 0;
         int it = 0;
         for (int u = cluster_id; u < num_units; u += num_clusters) {
@@ -297,17 +303,18 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err, 104);
                 ptx::tc_fence_after();
 
-                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN;
+                const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN + half * kColsPerWarp;
+                const uint32_t col0 = half * kColsPerWarp;
                 uint32_t va[32], vb[32];
                 ptx::tmem_ld_32x32(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < kTileN / 32; c += 2) {
+                for (int c = 0; c < kColsPerWarp / 32; c += 2) {
                     tmem_ld_wait_regs(va);
                     ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-                    filter_chunk(va, thr, p.row_base + row0 + c * 32, valid_cols - c * 32, my_stage, scnt, p, qc);
+                    filter_chunk(va, thr, p.row_base + row0 + col0 + c * 32, valid_cols - static_cast<int>(col0) - c * 32, my_stage, scnt, p, qc);
                     tmem_ld_wait_regs(vb);
-                    if (c + 2 < kTileN / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                    filter_chunk(vb, thr, p.row_base + row0 + (c + 1) * 32, valid_cols - (c + 1) * 32, my_stage, scnt, p, qc);
+                    if (c + 2 < kColsPerWarp / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                    filter_chunk(vb, thr, p.row_base + row0 + col0 + (c + 1) * 32, valid_cols - static_cast<int>(col0) - (c + 1) * 32, my_stage, scnt, p, qc);
                 }
                 // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
                 ptx::tc_fence_before();
