@@ -292,6 +292,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         // corpus tiles per work unit: 16 when the launch is large, fewer for the small early
         // chunks so that every CTA (pair) still gets at least ~4 units
         p.unit_tiles = 16;
+        if (const char* e = getenv("DRT_B200_UNIT_TILES")) { const int v = atoi(e); if (v >= 1 && v <= 256) p.unit_tiles = v; }
         while (p.unit_tiles > 1 &&
                (int64_t)p.num_m_tiles * ((p.n_tile_count + p.unit_tiles - 1) / p.unit_tiles) < 4ll * (s->sm_count / kctas))
             p.unit_tiles /= 2;
