@@ -244,12 +244,7 @@ def main():
     def step_device():
         if store is not None:
             D, I = index.search(q_dev, k, id_offset=store._offsets[rank], flags=flags)
-            Ds = [torch.empty_like(D) for _ in range(world)]
-            Is = [torch.empty_like(I) for _ in range(world)]
-            dist.all_gather(Ds, D)
-            dist.all_gather(Is, I)
-            from denseretrievaltoolkits_b200.store import _cuda_merge
-            return _cuda_merge(torch.stack(Ds), torch.stack(Is), k, sorted_unique=True)
+            return store._exchange_and_merge(D, I, k)     # same exchange + merge store.search() runs
         return index.search(q_dev, k, flags=flags)
 
     def step_host():

@@ -144,11 +144,7 @@ class ShardedCorpusStore:
                 D, I = torch.from_numpy(D), torch.from_numpy(I)
                 if dist.get_backend(self.group) == "nccl":
                     D, I = D.cuda(self.shards[0].device), I.cuda(self.shards[0].device)
-            Ds = [torch.empty_like(D) for _ in range(self.world)]
-            Is = [torch.empty_like(I) for _ in range(self.world)]
-            dist.all_gather(Ds, D, group=self.group)
-            dist.all_gather(Is, I, group=self.group)
-            Dm, Im = self._merge(torch.stack(Ds), torch.stack(Is), k)
+            Dm, Im = self._exchange_and_merge(D, I, k)
             if as_numpy:
                 return Dm.cpu().numpy(), Im.cpu().numpy()
             return Dm, Im
@@ -162,6 +158,34 @@ class ShardedCorpusStore:
         if as_numpy:
             return Dm.cpu().numpy(), Im.cpu().numpy()
         return Dm, Im
+
+    # candidate entries per rank above which the exchange switches from all-gather (every rank
+    # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged
+    # [Q/W, k] slices are all-gathered): W x fewer bytes received and W x less merge work
+    A2A_MIN_ENTRIES = 1 << 20
+
+    def _exchange_and_merge(self, D: torch.Tensor, I: torch.Tensor, k: int):
+        W = self.world
+        Q = D.shape[0]
+        if W >= 4 and Q * k >= self.A2A_MIN_ENTRIES and Q >= W:
+            per = -(-Q // W)
+            if per * W != Q:     # pad the query axis so it splits evenly; padding rows are dropped below
+                padD = torch.full((per * W - Q, k), -3.4028234663852886e38, dtype=D.dtype, device=D.device)
+                padI = torch.full((per * W - Q, k), -1, dtype=I.dtype, device=I.device)
+                D, I = torch.cat([D, padD]), torch.cat([I, padI])
+            rD, rI = torch.empty_like(D), torch.empty_like(I)
+            dist.all_to_all_single(rD, D.contiguous(), group=self.group)    # rD[g] = rank g's list for MY query slice
+            dist.all_to_all_single(rI, I.contiguous(), group=self.group)
+            mD, mI = self._merge(rD.view(W, per, k), rI.view(W, per, k), k)
+            oD, oI = torch.empty_like(D), torch.empty_like(I)
+            dist.all_gather_into_tensor(oD, mD.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(oI, mI.contiguous(), group=self.group)
+            return oD[:Q], oI[:Q]
+        Ds = [torch.empty_like(D) for _ in range(W)]
+        Is = [torch.empty_like(I) for _ in range(W)]
+        dist.all_gather(Ds, D, group=self.group)
+        dist.all_gather(Is, I, group=self.group)
+        return self._merge(torch.stack(Ds), torch.stack(Is), k)
 
     def search_local_queries(self, q_local, k: int):
         """Trainer.evaluate use (trainer.py:287-297): every rank holds its OWN query batch

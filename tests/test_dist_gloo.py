@@ -62,8 +62,11 @@ def _worker(rank, world, port, out_dir):
     t = torch.full((2, 3), float(rank), requires_grad=True)
     g = gather_rank_major(t, rank, world)
     g.sum().backward()
+    from denseretrievaltoolkits_b200.evaluation import reduce_metrics
+
+    red = reduce_metrics({"Recall@5": 2.0 + rank, "MRR@5": 1.0, "query_num": 0}, 3 + rank)   # per-rank sums
     np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, Dl=np.asarray(Dl), Il=np.asarray(Il),
-             g=g.detach().numpy(), grad=t.grad.numpy())
+             g=g.detach().numpy(), grad=t.grad.numpy(), red=np.array([red["Recall@5"], red["MRR@5"], red["query_num"]]))
     dist.destroy_process_group()
 
 
@@ -83,6 +86,8 @@ def test_sharded_store_two_ranks_gloo(tmp_path):
         # rank-major gather; gradient flows only into the local slot (biencoder.py:251)
         np.testing.assert_array_equal(r["g"], np.repeat([[0.0], [1.0]], 2, axis=0).repeat(3, axis=1).reshape(4, 3))
         np.testing.assert_array_equal(r["grad"], np.ones((2, 3)))
+        # metrics reduced across ranks: (2+3)/7 and (1+1)/7 over 3+4 queries (the reference never reduces)
+        np.testing.assert_allclose(r["red"], [5.0 / 7.0, 2.0 / 7.0, 7.0])
 
 
 def test_shard_offsets_rank_major():

@@ -160,7 +160,43 @@ def mining_goldens():
     print("mining cases", len(cases))
 
 
+def eval_goldens():
+    """has_answers (nq_eval.py:203-218) and get_metrics (metrics.py:50-59) run by the reference."""
+    from DRT.evaluator.metrics import get_metrics
+    from DRT.evaluator.nq_eval import has_answers
+
+    texts = [
+        "The Eiffel Tower was completed in 1889, in Paris (France).",
+        "Émile Zola wrote J'accuse…! in 1898; café culture thrived.",
+        "He scored 3-2 in the U.S. Open; it's a record-breaking 100m dash!",
+        "東京 is the capital of Japan. Tokyo-to has 14 million people.",
+        "",
+        "new york city, New York, NEW YORK",
+        "The answer is forty-two (42).",
+    ]
+    answers = [["Paris"], ["paris", "London"], ["1889"], ["Zola"], ["emile zola"], ["Émile Zola"], ["J'accuse"],
+               ["U.S. Open"], ["us open"], ["3-2"], ["100m"], ["東京"], ["tokyo-to"], [""], ["New York City"],
+               ["york new"], ["forty two"], ["(42)"], ["France)."], ["completed in 1889 ,"], ["café"], ["cafe"]]
+    cases = []
+    for t in texts:
+        for a in answers:
+            cases.append(dict(text=t, answers=a, regex=False, hit=bool(has_answers(t, a))))
+    for t, a in [(texts[0], [r"18\\d\\d"]), (texts[0], [r"paris|london"]), (texts[2], [r"\\d+-\\d+"]), (texts[2], ["(unclosed"]),
+                 (texts[1], [r"caf."])]:
+        cases.append(dict(text=t, answers=a, regex=True, hit=bool(has_answers(t, a, regex=True))))
+    rng = np.random.default_rng(77)
+    mcases = []
+    for Q, K, p, topk in [(6, 20, 0.15, [1, 5, 10, 20]), (16, 100, 0.03, [5, 10, 20, 50, 100]), (4, 10, 0.0, [1, 5, 10]),
+                          (5, 8, 0.9, [1, 3, 8, 20])]:
+        hits = (rng.random((Q, K)) < p).astype(np.int8)
+        m = get_metrics(hits, topk)
+        mcases.append(dict(hits=hits.tolist(), topk=topk, metrics={k: float(v) for k, v in m.items()}))
+    json.dump(dict(has_answers=cases, metrics=mcases), open(os.path.join(OUT, "evaluation.json"), "w"), ensure_ascii=False)
+    print("evaluation goldens:", len(cases), "has_answers cases,", sum(c["hit"] for c in cases), "hits;", len(mcases), "metric cases")
+
+
 if __name__ == "__main__":
+    eval_goldens()
     loss_goldens()
     merge_goldens()
     metrics_goldens()
