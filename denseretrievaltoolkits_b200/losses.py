@@ -112,6 +112,59 @@ class SimpleContrastiveLoss(nn.Module):
         return _InBatchCE.apply(x, y, target, reduction, False)[0]
 
 
+class _ShardedInBatchCE(torch.autograd.Function):
+    """Cross-device in-batch loss without the W-fold redundant work of the reference.
+
+    The reference all-gathers queries AND passages and every rank evaluates the whole
+    [B·W, P·W] loss (losses.py:28-34, biencoder.py:103-119).  Here only the passages are
+    gathered; rank r evaluates its own B rows against all P·W passages (targets shifted by the
+    rank's row offset), the per-rank loss sums are all-reduced, and in the backward the passage
+    gradient contributions dlogitsᵀ·x_local of all ranks are reduce-scattered.  Values and
+    gradients equal the reference's (same sums, 1/W of the FLOPs per rank)."""
+
+    @staticmethod
+    def forward(ctx, x: Tensor, y: Tensor, group, rank: int, world: int, scale_loss: bool):
+        lib = _lib.load()
+        xc, yc = _f32c(x), _f32c(y)
+        B, d = xc.shape
+        P = yc.shape[0]
+        dev = xc.device
+        y_all = torch.empty((world * P, d), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(y_all, yc, group=group)
+        tpq = (world * P) // (world * B)                                   # losses.py:13 on the gathered shapes
+        target = (torch.arange(B, device=dev, dtype=torch.int64) + rank * B) * tpq
+        lse = torch.empty((B,), dtype=torch.float32, device=dev)
+        out = torch.empty((B + 1,), dtype=torch.float32, device=dev)
+        base = out.data_ptr()
+        _lib.check(lib.drt_inbatch_ce_fwd(xc.data_ptr(), y_all.data_ptr(), B, world * P, d, target.data_ptr(), 1.0, None,
+                                          lse.data_ptr(), base, base + 4 * B, dev.index,
+                                          _lib.current_stream_ptr(dev.index)), "inbatch_ce_fwd")
+        total = out[B:].clone()
+        dist.all_reduce(total, group=group)
+        coef = (float(world) if scale_loss else 1.0) / float(world * B)    # mean over all rows (x world_size)
+        ctx.save_for_backward(xc, y_all, lse, target)
+        ctx.meta = (group, rank, world, P, coef, x.dtype, y.dtype)
+        return (total * coef).reshape(())
+
+    @staticmethod
+    def backward(ctx, grad_loss: Tensor):
+        xc, y_all, lse, target = ctx.saved_tensors
+        group, rank, world, P, coef, xdt, ydt = ctx.meta
+        lib = _lib.load()
+        B, d = xc.shape
+        dev = xc.device
+        g = _f32c(grad_loss).reshape(1)
+        work = torch.empty((B, world * P), dtype=torch.float32, device=dev)
+        dx = torch.empty_like(xc)
+        dy_all = torch.empty_like(y_all)
+        _lib.check(lib.drt_inbatch_ce_bwd(xc.data_ptr(), y_all.data_ptr(), B, world * P, d, target.data_ptr(), lse.data_ptr(),
+                                          g.data_ptr(), 0, coef, work.data_ptr(), dx.data_ptr(), dy_all.data_ptr(),
+                                          dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_bwd")
+        dy = torch.empty((P, d), dtype=torch.float32, device=dev)
+        dist.reduce_scatter_tensor(dy, dy_all, group=group)
+        return dx.to(xdt), dy.to(ydt), None, None, None, None
+
+
 class DistributedContrastiveLoss(SimpleContrastiveLoss):
     def __init__(self, n_target: int = 0, scale_loss: bool = True):
         assert dist.is_initialized(), "Distributed training has not been properly initialized."
@@ -121,6 +174,9 @@ class DistributedContrastiveLoss(SimpleContrastiveLoss):
         self.scale_loss = scale_loss
 
     def forward(self, x: Tensor, y: Tensor, **kwargs):
+        if not kwargs and x.is_cuda and dist.get_backend() == "nccl":
+            # default target / mean reduction: the sharded evaluation (1/W of the work per rank)
+            return _ShardedInBatchCE.apply(x, y, None, self.rank, self.word_size, self.scale_loss)
         dist_x = self.gather_tensor(x)
         dist_y = self.gather_tensor(y)
         loss = super().forward(dist_x, dist_y, **kwargs)
