@@ -130,6 +130,7 @@ struct DevBuf {
 };
 
 int next_pow2(int n) { int p = 1; while (p < n) p <<= 1; return p; }
+inline bool aligned16_ptr(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 }  // namespace
 
@@ -148,9 +149,10 @@ struct drt_store {
     int* err_host = nullptr;     // pinned + mapped: kernel watchdog code
     int* err_dev = nullptr;
     int64_t* misc_host = nullptr;  // pinned: [0] overflow flag [1] flagged count
-    int64_t stats[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int64_t stats[12] = {0};
     bool attrs_set = false;
     std::vector<cudaEvent_t> ev;   // per-launch timing events (DRT_SEARCH_TIME_KERNELS)
+    int64_t exact_queries = 0;     // queries of the last search that needed the exact fp32 first pass
 };
 
 namespace {
@@ -269,8 +271,9 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         drt::init_query_state_kernel<<<(int)((nq + 255) / 256), 256, 0, st>>>(thr, cnt, (int)nq);
         s->stats[0] += 2;
     }
+    const bool exact_pass = (kctas == 0);    // fp32 SIMT first pass (last-resort refinement)
     CUtensorMap tmap_q;
-    if ((rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
+    if (!exact_pass && (rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
 
     const std::vector<Chunk> chunks = plan_chunks(s->ntotal, s->seg_rows, cap, keep, attempt);
     s->stats[6] = (int64_t)chunks.size();
@@ -280,6 +283,18 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     bool frozen = false;
     for (const Chunk& c : chunks) {
         const int64_t seg_valid = std::min<int64_t>(s->seg_rows, s->ntotal - (int64_t)c.seg * s->seg_rows);
+        if (exact_pass) {
+            using C = drt::GemmLarge;
+            const int64_t nrows = c.row1 - c.row0;
+            const float* rows = s->seg_f32[c.seg] + (size_t)c.row0 * dim;
+            dim3 grid((unsigned)((nrows + C::BN - 1) / C::BN), (unsigned)((nq + C::BM - 1) / C::BM));
+            drt::exact_filter_kernel<C><<<grid, C::THREADS, 0, st>>>(
+                q_dev, (long long)nq, rows, (long long)nrows, dim, (uint32_t)((int64_t)c.seg * s->seg_rows + c.row0), thr,
+                cnt, cand, (uint32_t)cap, aligned16_ptr(q_dev) ? 1 : 0);
+            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
+            s->stats[0] += 2;
+            continue;
+        }
         if (c.seg != tmap_seg) {
             if ((rc = make_tmap_bf16(&tmap_d, s->seg_bf16[c.seg], (uint64_t)seg_valid, (uint64_t)dim,
                                      drt::kTileN / kctas)) != DRT_OK) return rc;
@@ -334,7 +349,8 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         drt::rescore_kernel<<<(int)nq, 256, smem, st>>>(cand, cnt, (uint32_t)cap, (uint32_t)keep, q_dev, dim,
                                                        (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
                                                        (long long)id_offset, out_s, (long long*)out_i,
-                                                       (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag);
+                                                       (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag,
+                                                       exact_pass ? 0 : 1);
         s->stats[0] += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -406,6 +422,39 @@ int refine_flagged(drt_store* s, const float* q_dev, int64_t nq, int k, float* o
         s->stats[0] += 2;
         *flagged = still;
     }
+    return DRT_OK;
+}
+
+// Last resort for queries the bf16 pass cannot certify: first pass in exact fp32 (SIMT).
+int exact_flagged(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
+                  int64_t id_offset, uint32_t flags, cudaStream_t st, unsigned char* qflag, int64_t* flagged) {
+    std::vector<unsigned char> hflag((size_t)nq);
+    CUDA_TRY(cudaMemcpyAsync(hflag.data(), qflag, (size_t)nq, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    std::vector<int> idx;
+    for (int64_t i = 0; i < nq; ++i) if (hflag[i]) idx.push_back((int)i);
+    const int64_t nf = (int64_t)idx.size();
+    if (nf == 0) { *flagged = 0; return DRT_OK; }
+    int rc;
+    if ((rc = s->sub_idx.ensure((size_t)nf * 4)) != DRT_OK) return rc;
+    if ((rc = s->sub_q.ensure((size_t)nf * s->dim * 4)) != DRT_OK) return rc;
+    if ((rc = s->sub_os.ensure((size_t)nf * k * 4)) != DRT_OK) return rc;
+    if ((rc = s->sub_oi.ensure((size_t)nf * k * 8)) != DRT_OK) return rc;
+    if ((rc = s->sub_flag.ensure((size_t)nf)) != DRT_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(s->sub_idx.p, idx.data(), (size_t)nf * 4, cudaMemcpyHostToDevice, st));
+    drt::gather_rows_kernel<<<(int)std::min<int64_t>(nf, 4096), 192, 0, st>>>(
+        q_dev, (const int*)s->sub_idx.p, (float*)s->sub_q.p, s->dim, (int)nf);
+    int64_t still = 0;
+    rc = search_retrying(s, (const float*)s->sub_q.p, nf, k, (float*)s->sub_os.p, (int64_t*)s->sub_oi.p, id_offset,
+                         flags, st, /*kctas=*/0, 0, (unsigned char*)s->sub_flag.p, &still);
+    if (rc != DRT_OK) return rc;
+    drt::scatter_results_kernel<<<(int)std::min<int64_t>(nf, 4096), 128, 0, st>>>(
+        (const float*)s->sub_os.p, (const long long*)s->sub_oi.p, (const unsigned char*)s->sub_flag.p,
+        (const int*)s->sub_idx.p, out_s, (long long*)out_i, qflag, k, (int)nf);
+    CUDA_TRY(cudaGetLastError());
+    s->stats[0] += 2;
+    s->exact_queries += nf;
+    *flagged = still;
     return DRT_OK;
 }
 
@@ -550,7 +599,8 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
     DeviceGuard g(s->device);
     if ((rc = set_kernel_attrs(s)) != DRT_OK) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    for (int i = 0; i < 8; ++i) s->stats[i] = 0;
+    for (int i = 0; i < 12; ++i) s->stats[i] = 0;
+    s->exact_queries = 0;
 
     // CTA-pair tiles (M=256) halve the corpus-operand smem/L2 traffic per FLOP; with <= 128
     // queries half of a pair tile would be padding and the pass is HBM-bound anyway.
@@ -590,6 +640,8 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
                                  (unsigned char*)s->qflag.p, &flagged);
             if (rc == DRT_OK && flagged > 0 && !(flags & DRT_SEARCH_NO_RESCORE)) {
                 rc = refine_flagged(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, (unsigned char*)s->qflag.p, &flagged);
+                if (rc == DRT_OK && flagged > 0)
+                    rc = exact_flagged(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, (unsigned char*)s->qflag.p, &flagged);
             }
             s->stats[4] += flagged;
             if (rc != DRT_OK) return rc;
@@ -628,9 +680,10 @@ int drt_plan_params(int k, int attempt, int* kprime, int* cap_out) {
     return DRT_OK;
 }
 
-int drt_search_stats(const drt_store* s, int64_t out[8]) {
+int drt_search_stats(const drt_store* s, int64_t out[12]) {
     if (!s || !out) return fail(DRT_E_INVALID, "bad arguments");
-    for (int i = 0; i < 8; ++i) out[i] = s->stats[i];
+    for (int i = 0; i < 12; ++i) out[i] = s->stats[i];
+    out[8] = s->exact_queries;
     return DRT_OK;
 }
 

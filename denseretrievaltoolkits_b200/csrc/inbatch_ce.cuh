@@ -23,36 +23,38 @@
 
 namespace drt {
 
-constexpr int kGemmBK = 16;
-
 struct GemmOperand {
     const float* p;
     long long s_outer;   // stride of the non-k index (m for A, n for B)
     long long s_k;       // stride of k
 };
 
-// Tile config: BM x BN outputs, TM x TN per thread, threads = (BM/TM) * (BN/TN)
-template <int BM_, int BN_, int TM_, int TN_>
+// Tile config: BM x BN outputs, TM x TN per thread, threads = (BM/TM) * (BN/TN), k-slab depth BK.
+// The slab must be deep enough that its FMAs cover the L2 latency of the next slab's loads
+// (with BK = 16 a 32x32 tile spent ~85 % of its time waiting for them).
+template <int BM_, int BN_, int TM_, int TN_, int BK_>
 struct GemmCfg {
-    static constexpr int BM = BM_, BN = BN_, TM = TM_, TN = TN_;
+    static constexpr int BM = BM_, BN = BN_, TM = TM_, TN = TN_, BK = BK_;
     static constexpr int TX = BN / TN, TY = BM / TM, THREADS = TX * TY;
     static constexpr int PAD = 4;
+    static constexpr int VA = BM * BK / 4 / THREADS, VB = BN * BK / 4 / THREADS;   // float4 per thread per slab
+    static_assert(VA * 4 * THREADS == BM * BK && VB * 4 * THREADS == BN * BK, "slab must split into whole float4s");
 };
-using GemmSmall = GemmCfg<32, 32, 4, 2>;    // 128 threads
-using GemmLarge = GemmCfg<64, 64, 4, 4>;    // 256 threads
+using GemmSmall = GemmCfg<32, 32, 4, 2, 64>;    // 128 threads, 36 KB smem
+using GemmLarge = GemmCfg<64, 64, 4, 4, 32>;    // 256 threads, 34 KB smem
 
-// One thread moves one float4 of a [ROWS x kGemmBK] operand tile per k-slab (ROWS*kGemmBK/4 ==
-// THREADS).  Element (r, k) lives at p[(r0 + r) * s_outer + (k0 + k) * s_k]; out-of-range -> 0.
-// fetch_vec issues the global load into registers; store_vec writes it into smem laid out
-// [k][row] (row contiguous) -- split so the load latency overlaps the FMAs of the current slab.
-template <int ROWS>
-__device__ __forceinline__ void fetch_vec(float (&v)[4], const GemmOperand& op, long long r0, long long nrows,
+// Vector v (of NV per thread) of a [ROWS x BK] operand tile.  Element (r, k) lives at
+// p[(r0 + r) * s_outer + (k0 + k) * s_k]; out-of-range -> 0.  fetch issues the global load into
+// registers; store writes it into smem laid out [k][row] (row contiguous) -- split so the load
+// latency overlaps the FMAs of the current slab.
+template <int ROWS, int BK, int THREADS>
+__device__ __forceinline__ void fetch_vec(float (&v)[4], int vi, const GemmOperand& op, long long r0, long long nrows,
                                           long long k0, long long K, bool vec_ok) {
-    const int t = threadIdx.x;
+    const int i = vi * THREADS + threadIdx.x;
     v[0] = v[1] = v[2] = v[3] = 0.f;
     if (op.s_k == 1) {            // k contiguous: 4 consecutive k of one row
-        constexpr int VEC_PER_ROW = kGemmBK / 4;
-        const int r = t / VEC_PER_ROW, kk = (t % VEC_PER_ROW) * 4;
+        constexpr int VEC_PER_ROW = BK / 4;
+        const int r = i / VEC_PER_ROW, kk = (i % VEC_PER_ROW) * 4;
         const long long gr = r0 + r, gk = k0 + kk;
         if (gr < nrows) {
             const float* src = op.p + gr * op.s_outer + gk;
@@ -66,7 +68,7 @@ __device__ __forceinline__ void fetch_vec(float (&v)[4], const GemmOperand& op, 
         }
     } else {                      // row index contiguous: 4 consecutive rows of one k
         constexpr int VEC_PER_K = ROWS / 4;
-        const int kk = t / VEC_PER_K, r = (t % VEC_PER_K) * 4;
+        const int kk = i / VEC_PER_K, r = (i % VEC_PER_K) * 4;
         const long long gr = r0 + r, gk = k0 + kk;
         if (gk < K) {
             const float* src = op.p + gk * op.s_k + gr;
@@ -80,17 +82,17 @@ __device__ __forceinline__ void fetch_vec(float (&v)[4], const GemmOperand& op, 
         }
     }
 }
-template <int ROWS, int LD>
-__device__ __forceinline__ void store_vec(float (*dst)[LD], const float (&v)[4], bool k_contiguous) {
-    const int t = threadIdx.x;
+template <int ROWS, int BK, int THREADS, int LD>
+__device__ __forceinline__ void store_vec(float (*dst)[LD], const float (&v)[4], int vi, bool k_contiguous) {
+    const int i = vi * THREADS + threadIdx.x;
     if (k_contiguous) {
-        constexpr int VEC_PER_ROW = kGemmBK / 4;
-        const int r = t / VEC_PER_ROW, kk = (t % VEC_PER_ROW) * 4;
+        constexpr int VEC_PER_ROW = BK / 4;
+        const int r = i / VEC_PER_ROW, kk = (i % VEC_PER_ROW) * 4;
 #pragma unroll
         for (int j = 0; j < 4; ++j) dst[kk + j][r] = v[j];
     } else {
         constexpr int VEC_PER_K = ROWS / 4;
-        const int kk = t / VEC_PER_K, r = (t % VEC_PER_K) * 4;
+        const int kk = i / VEC_PER_K, r = (i % VEC_PER_K) * 4;
         *reinterpret_cast<float4*>(&dst[kk][r]) = make_float4(v[0], v[1], v[2], v[3]);
     }
 }
@@ -102,31 +104,32 @@ template <class Cfg>
 __device__ __forceinline__ void gemm_tile(const GemmOperand& A, const GemmOperand& B, long long M, long long N,
                                           long long K, long long m0, long long n0, bool vecA, bool vecB,
                                           float (&acc)[Cfg::TM][Cfg::TN]) {
-    constexpr int BM = Cfg::BM, BN = Cfg::BN, TM = Cfg::TM, TN = Cfg::TN;
-    static_assert(BM * kGemmBK / 4 == Cfg::THREADS && BN * kGemmBK / 4 == Cfg::THREADS, "one float4 per thread per slab");
-    __shared__ __align__(16) float sa[2][kGemmBK][BM + Cfg::PAD];
-    __shared__ __align__(16) float sb[2][kGemmBK][BN + Cfg::PAD];
+    constexpr int BM = Cfg::BM, BN = Cfg::BN, TM = Cfg::TM, TN = Cfg::TN, BK = Cfg::BK, T = Cfg::THREADS;
+    __shared__ __align__(16) float sa[2][BK][BM + Cfg::PAD];
+    __shared__ __align__(16) float sb[2][BK][BN + Cfg::PAD];
     const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
     const bool a_kc = A.s_k == 1, b_kc = B.s_k == 1;
 #pragma unroll
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-    float ra[4], rb[4];
-    fetch_vec<BM>(ra, A, m0, M, 0, K, vecA);
-    fetch_vec<BN>(rb, B, n0, N, 0, K, vecB);
-    store_vec<BM>(sa[0], ra, a_kc);
-    store_vec<BN>(sb[0], rb, b_kc);
+    float ra[Cfg::VA][4], rb[Cfg::VB][4];
+#pragma unroll
+    for (int v = 0; v < Cfg::VA; ++v) { fetch_vec<BM, BK, T>(ra[v], v, A, m0, M, 0, K, vecA); store_vec<BM, BK, T>(sa[0], ra[v], v, a_kc); }
+#pragma unroll
+    for (int v = 0; v < Cfg::VB; ++v) { fetch_vec<BN, BK, T>(rb[v], v, B, n0, N, 0, K, vecB); store_vec<BN, BK, T>(sb[0], rb[v], v, b_kc); }
     __syncthreads();
     int buf = 0;
-    for (long long k0 = 0; k0 < K; k0 += kGemmBK) {
-        const bool more = k0 + kGemmBK < K;
+    for (long long k0 = 0; k0 < K; k0 += BK) {
+        const bool more = k0 + BK < K;
         if (more) {               // global loads of the next slab fly while this slab is multiplied
-            fetch_vec<BM>(ra, A, m0, M, k0 + kGemmBK, K, vecA);
-            fetch_vec<BN>(rb, B, n0, N, k0 + kGemmBK, K, vecB);
+#pragma unroll
+            for (int v = 0; v < Cfg::VA; ++v) fetch_vec<BM, BK, T>(ra[v], v, A, m0, M, k0 + BK, K, vecA);
+#pragma unroll
+            for (int v = 0; v < Cfg::VB; ++v) fetch_vec<BN, BK, T>(rb[v], v, B, n0, N, k0 + BK, K, vecB);
         }
 #pragma unroll
-        for (int kk = 0; kk < kGemmBK; ++kk) {
+        for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
             const float4 a4 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * TM]);
             a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
@@ -143,8 +146,10 @@ __device__ __forceinline__ void gemm_tile(const GemmOperand& A, const GemmOperan
                 for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
         }
         if (more) {
-            store_vec<BM>(sa[buf ^ 1], ra, a_kc);
-            store_vec<BN>(sb[buf ^ 1], rb, b_kc);
+#pragma unroll
+            for (int v = 0; v < Cfg::VA; ++v) store_vec<BM, BK, T>(sa[buf ^ 1], ra[v], v, a_kc);
+#pragma unroll
+            for (int v = 0; v < Cfg::VB; ++v) store_vec<BN, BK, T>(sb[buf ^ 1], rb[v], v, b_kc);
         }
         __syncthreads();
         buf ^= 1;
@@ -213,9 +218,25 @@ inbatch_ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, 
     const int ncol = gridDim.x;
     for (long long i = threadIdx.x; i < B; i += Cfg::THREADS) {
         float m = -FLT_MAX;
-        for (int c = 0; c < ncol; ++c) m = fmaxf(m, __ldcg(part_max + i * ncol + c));
+        for (int c0 = 0; c0 < ncol; c0 += 8) {      // 8 independent loads in flight per step
+            float pm[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) pm[u] = (c0 + u < ncol) ? __ldcg(part_max + i * ncol + c0 + u) : -FLT_MAX;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) m = fmaxf(m, pm[u]);
+        }
         float s = 0.f;
-        for (int c = 0; c < ncol; ++c) s += __ldcg(part_sum + i * ncol + c) * expf(__ldcg(part_max + i * ncol + c) - m);
+        for (int c0 = 0; c0 < ncol; c0 += 8) {
+            float pm[8], ps[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool in = c0 + u < ncol;
+                pm[u] = in ? __ldcg(part_max + i * ncol + c0 + u) : -FLT_MAX;
+                ps[u] = in ? __ldcg(part_sum + i * ncol + c0 + u) : 0.f;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) s += ps[u] * expf(pm[u] - m);
+        }
         const float lse = m + logf(s);
         const long long tc = target ? target[i] : i * target_stride;
         // an out-of-range target poisons the loss instead of reading a stale logit

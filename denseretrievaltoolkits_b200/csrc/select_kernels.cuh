@@ -7,6 +7,7 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <cfloat>
+#include "inbatch_ce.cuh"
 #include "mips_filter.cuh"
 
 namespace drt {
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(256)
 rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t keep,
                const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
                int k, long long id_offset, float* out_scores, long long* out_ids,
-               int do_rescore, unsigned long long* flagged, unsigned char* qflag) {
+               int do_rescore, unsigned long long* flagged, unsigned char* qflag, int check) {
     extern __shared__ uint64_t s_keys[];            // [P] then dim floats
     const int q = blockIdx.x;
     const int n = static_cast<int>(min(min(cnt[q], cap), keep));
@@ -192,7 +193,7 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
     // exact k-th score, a non-candidate could belong to the top-k: count the query as flagged.
     if (threadIdx.x == 0) {
         bool flag = false;
-        if (do_rescore && n == static_cast<int>(keep) && n >= k && s_keys[k - 1] != 0ull) {
+        if (check && do_rescore && n == static_cast<int>(keep) && n >= k && s_keys[k - 1] != 0ull) {
             const float tau = ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32));
             const float amin = ordered_to_float(s_amin);
             const float emax = __uint_as_float(s_emax);
@@ -219,6 +220,38 @@ __global__ void scatter_results_kernel(const float* __restrict__ ss, const long 
         const size_t d = static_cast<size_t>(idx[r]) * k, s = static_cast<size_t>(r) * k;
         for (int j = threadIdx.x; j < k; j += blockDim.x) { os[d + j] = ss[s + j]; oi[d + j] = si[s + j]; }
         if (threadIdx.x == 0) qf[idx[r]] = sf[r];
+    }
+}
+
+// Exact first pass (last-resort refinement): fp32 FFMA scores of a few queries against a chunk of
+// the fp32 plane, fed into the same threshold / candidate-list machinery as K1.  Used only for
+// queries whose exactness check still fails after the bf16 pass was repeated with larger k'
+// (e.g. a corpus of near-duplicates whose score gaps are below bf16 resolution), so every
+// returned result is either margin-checked or computed from exact scores.
+template <class Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS)
+exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __restrict__ rows, long long nrows,
+                    int dim, uint32_t row_id0, const float* __restrict__ thr, uint32_t* cnt, uint64_t* cand,
+                    uint32_t cap, int vec_ok) {
+    constexpr int TM = Cfg::TM, TN = Cfg::TN;
+    const long long m0 = static_cast<long long>(blockIdx.y) * Cfg::BM;
+    const long long n0 = static_cast<long long>(blockIdx.x) * Cfg::BN;
+    float acc[TM][TN];
+    gemm_tile<Cfg>(GemmOperand{q, dim, 1}, GemmOperand{rows, dim, 1}, nq, nrows, dim, m0, n0, vec_ok, vec_ok, acc);
+    const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+        const long long qi = m0 + ty * TM + i;
+        if (qi >= nq) continue;
+        const float t = thr[qi];
+#pragma unroll
+        for (int j = 0; j < TN; ++j) {
+            const long long col = n0 + tx * TN + j;
+            if (col < nrows && acc[i][j] > t) {
+                const uint32_t slot = atomicAdd(cnt + qi, 1u);
+                if (slot < cap) cand[static_cast<size_t>(qi) * cap + slot] = pack_key(acc[i][j], row_id0 + static_cast<uint32_t>(col));
+            }
+        }
     }
 }
 

@@ -131,10 +131,10 @@ class IndexFlatIP:
         return D, I
 
     def search_stats(self) -> dict:
-        buf = (ctypes.c_int64 * 8)()
+        buf = (ctypes.c_int64 * 12)()
         _lib.check(self._lib.drt_search_stats(self._h, buf), "search_stats")
         names = ["launches", "filter_launches", "overflow_retries", "kprime", "flagged_queries",
-                 "ctas_per_tile", "chunks", "filter_ns"]
+                 "ctas_per_tile", "chunks", "filter_ns", "exact_queries"]
         return dict(zip(names, [int(v) for v in buf]))
 
     # ---- reconstruct ------------------------------------------------------------------------

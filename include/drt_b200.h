@@ -92,8 +92,9 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k,
  *  [0] kernel launches  [1] mma-filter launches  [2] candidate-buffer overflow retries
  *  [3] first-pass candidates per query (k')      [4] queries whose exactness check flagged
  *  [5] ctas per tile (1|2)                        [6] corpus chunks
- *  [7] summed device time of the MMA-filter launches in ns (DRT_SEARCH_TIME_KERNELS only)   */
-int drt_search_stats(const drt_store* s, int64_t out[8]);
+ *  [7] summed device time of the MMA-filter launches in ns (DRT_SEARCH_TIME_KERNELS only)
+ *  [8] queries that needed the exact fp32 first pass (last-resort refinement)  [9..11] reserved */
+int drt_search_stats(const drt_store* s, int64_t out[12]);
 
 /* Host-side planning, exposed for tests (no device needed).  drt_plan_params: k' (first-pass
  * candidates kept per query) and the candidate-buffer capacity for retry level `attempt`.

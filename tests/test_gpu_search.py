@@ -277,3 +277,45 @@ def test_scale_properties_2m_rows(k):
     torch.testing.assert_close(D[sub], best_d, rtol=RTOL, atol=1e-3)
     D2, I2 = index.search(q, k)
     assert torch.equal(I, I2) and torch.equal(D, D2)
+
+
+@pytest.mark.parametrize("d", [64, 128, 384, 1024])
+def test_other_embedding_dims(d):
+    """dim is any multiple of 64 (one 128-byte bf16 swizzle span): MiniLM 384, BERT-large 1024..."""
+    rng = np.random.default_rng(d)
+    x = rng.standard_normal((30000, d), dtype=np.float32)
+    q = rng.standard_normal((150, d), dtype=np.float32)
+    index = _mk(d=d, seg_rows=8192)
+    index.add(x)
+    D, I = index.search(q, 50)
+    Dr, Ir = flat_ip.flat_ip_search(x, q, 50)
+    _check_parity(D, I, Dr, Ir, 50, 30000, scale=np.sqrt(float(d)))
+    from denseretrievaltoolkits_b200 import faiss_compat
+
+    with pytest.raises(RuntimeError):
+        faiss_compat.IndexFlatIP(100)          # not a multiple of 64: refused, no fallback
+
+
+def test_near_duplicate_corpus_falls_back_to_exact_fp32_pass():
+    """Score gaps far below bf16 resolution: the margin check cannot certify the bf16 pass, so
+    the flagged queries go through a larger k' and finally the exact fp32 first pass; the
+    result is still the exact top-k."""
+    n, d = 40000, 768
+    rng = np.random.default_rng(11)
+    u = rng.standard_normal(d).astype(np.float32)
+    x = (u[None, :] * (1.0 + 1e-5 * rng.standard_normal((n, 1)).astype(np.float32))
+         + 1e-4 * rng.standard_normal((n, d)).astype(np.float32)).astype(np.float32)
+    q = (u[None, :] + 0.05 * rng.standard_normal((6, d))).astype(np.float32)
+    index = _mk(seg_rows=1 << 14)
+    index.add(x)
+    D, I = index.search(q, 50)
+    st = index.search_stats()
+    assert st["exact_queries"] > 0 and st["flagged_queries"] == 0, st
+    Dr, Ir = flat_ip.flat_ip_search_f64(x, q, 50)
+    # every returned row's exact (float64) score is within fp32 rounding of the true 50-th best
+    s64 = q.astype(np.float64) @ x.astype(np.float64).T
+    for r in range(6):
+        kth = Dr[r, 49]
+        got = s64[r, I[r]]
+        assert (got >= kth - 1e-4 * abs(kth)).all()
+        np.testing.assert_allclose(D[r], np.sort(got)[::-1], rtol=1e-4)
