@@ -276,7 +276,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     if (!exact_pass && (rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
 
     const std::vector<Chunk> chunks = plan_chunks(s->ntotal, s->seg_rows, cap, keep, attempt);
-    s->stats[6] = (int64_t)chunks.size();
+    if (keep_override == 0 && !exact_pass) s->stats[6] = (int64_t)chunks.size();
     CUtensorMap tmap_d;
     int tmap_seg = -1;
     size_t n_timed = 0;
@@ -362,7 +362,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         return fail(code ? DRT_E_INTERNAL : DRT_E_CUDA, "search kernels failed: %s (watchdog code %d)",
                     cudaGetErrorString(e), code);
     }
-    if (keep_override == 0) { s->stats[3] = keep; s->stats[5] = kctas; }
+    if (keep_override == 0 && !exact_pass) { s->stats[3] = keep; s->stats[5] = kctas; }
     for (size_t i = 0; i < n_timed; ++i) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]) == cudaSuccess) s->stats[7] += (int64_t)(ms * 1e6);
