@@ -314,3 +314,29 @@ def test_near_duplicate_corpus_falls_back_to_exact_fp32_pass():
     Dr, Ir = flat_ip.flat_ip_search_f64(x, q, 50)
     np.testing.assert_array_equal(I, Ir)
     np.testing.assert_array_equal(D.astype(np.float64), Dr)
+
+
+def test_randomised_shapes_against_oracle():
+    """Seeded fuzz over (nq, n, k, seg_rows, dim, #adds): tile / segment / chunk boundaries,
+    k > n, single rows, CTA-variant switch at 128 queries."""
+    rng = np.random.default_rng(2024)
+    cases = [(1, 1, 1, 256, 64), (129, 257, 3, 256, 64), (128, 256, 256, 256, 64), (127, 65537, 100, 16384, 64)]
+    for _ in range(26):
+        d = int(rng.choice([64, 128]))
+        cases.append((int(rng.integers(1, 600)), int(rng.integers(1, 70000)), int(rng.integers(1, 300)),
+                      int(rng.choice([256, 1024, 4096, 16384])), d))
+    for nq, n, k, seg_rows, d in cases:
+        x = rng.standard_normal((n, d), dtype=np.float32)
+        if n > 50 and rng.random() < 0.3:
+            x[-(n // 10):] = x[: n // 10]             # exact duplicates -> ties
+        q = rng.standard_normal((nq, d), dtype=np.float32)
+        index = _mk(d=d, seg_rows=seg_rows)
+        for part in np.array_split(x, int(rng.integers(1, 5))):
+            if part.shape[0]:
+                index.add(part)
+        D, I = index.search(q, k)
+        Dr, Ir = flat_ip.flat_ip_search(x, q, k)
+        try:
+            _check_parity(D, I, Dr, Ir, k, n, scale=np.sqrt(float(d)))
+        except AssertionError as e:
+            raise AssertionError(f"case nq={nq} n={n} k={k} seg_rows={seg_rows} d={d}: {e}") from e
