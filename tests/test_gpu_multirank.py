@@ -1,0 +1,34 @@
+"""GPU, >= 2 devices (skipped on a single-GPU box): the real NCCL paths — sharded store search
+(all-gather and all-to-all exchange + merge kernel) and the sharded distributed loss — launched
+as torchrun world-size-2 jobs."""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _torchrun(script, port):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", str(port), os.path.join(ROOT, "tools", script)]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    assert p.returncode == 0 and len(lines) == 2, p.stdout[-2000:] + p.stderr[-2000:]
+    return lines
+
+
+def test_sharded_search_two_ranks_nccl():
+    for r in _torchrun("dist_search_check.py", 29811):
+        assert r["ok"], r
+
+
+def test_sharded_distributed_loss_two_ranks_nccl():
+    for r in _torchrun("dist_loss_check.py", 29812):
+        assert r["ok"], r

@@ -1,0 +1,56 @@
+"""torchrun -N ranks: ShardedCorpusStore (NCCL candidate exchange + merge kernel) against a single
+full index built on every rank: ids bit for bit, scores bit for bit, both exchange modes.
+Run: torchrun --nproc-per-node N tools/dist_search_check.py"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np
+import torch
+import torch.distributed as dist
+
+rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(lr)
+dev = torch.device("cuda", lr)
+dist.init_process_group("nccl", device_id=dev)
+from denseretrievaltoolkits_b200 import faiss_compat
+from denseretrievaltoolkits_b200.store import ShardedCorpusStore
+
+n, d, nq = 300_000, 768, 1000
+g = torch.Generator(device=dev).manual_seed(5)          # same corpus on every rank
+x = torch.randn(n, d, device=dev, generator=g)
+x[-500:] = x[:500]                                        # ties across shards
+q = torch.randn(nq, d, device=dev, generator=g)
+full = faiss_compat.IndexFlatIP(d, device=lr, seg_rows=1 << 16)
+full.add(x)
+bounds = np.linspace(0, n, world + 1).astype(int)
+bounds[1:-1] += np.arange(1, world) * 37                  # uneven shards
+store = ShardedCorpusStore(d, device=lr, seg_rows=1 << 15)
+store.add(x[bounds[rank]:bounds[rank + 1]])
+offs = store.finalize()
+ok = offs == [int(b) for b in bounds]
+res = {"rank": rank, "world": world, "offsets_ok": ok}
+for k in (100, 1000):
+    Df, If = full.search(q, k)
+    for mode, thr in (("all_gather", 1 << 62), ("all_to_all", 0)):
+        store.A2A_MIN_ENTRIES = thr
+        D, I = store.search(q, k)
+        same = bool(torch.equal(I, If) and torch.equal(D, Df))
+        res[f"k{k}_{mode}"] = same
+        ok = ok and same
+    per = nq // world
+    Dl, Il = store.search_local_queries(q[rank * per:(rank + 1) * per].contiguous(), k)
+    same = bool(torch.equal(Il, If[rank * per:(rank + 1) * per]))
+    res[f"k{k}_local_queries"] = same
+    ok = ok and same
+Dn, In = store.search(q.cpu().numpy(), 100)               # host-buffer API
+Df, If = full.search(q, 100)
+res["numpy_api"] = bool(np.array_equal(In, If.cpu().numpy()))
+ok = ok and res["numpy_api"]
+res["ok"] = ok
+print(json.dumps(res), flush=True)
+dist.barrier()
+dist.destroy_process_group()
+sys.exit(0 if ok else 1)
