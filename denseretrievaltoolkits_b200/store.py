@@ -163,11 +163,12 @@ class ShardedCorpusStore:
     # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged
     # [Q/W, k] slices are all-gathered): W x fewer bytes received and W x less merge work
     A2A_MIN_ENTRIES = 1 << 20
+    A2A_MIN_WORLD = 4
 
     def _exchange_and_merge(self, D: torch.Tensor, I: torch.Tensor, k: int):
         W = self.world
         Q = D.shape[0]
-        if W >= 4 and Q * k >= self.A2A_MIN_ENTRIES and Q >= W:
+        if W >= self.A2A_MIN_WORLD and Q * k >= self.A2A_MIN_ENTRIES and Q >= W:
             per = -(-Q // W)
             if per * W != Q:     # pad the query axis so it splits evenly; padding rows are dropped below
                 padD = torch.full((per * W - Q, k), -3.4028234663852886e38, dtype=D.dtype, device=D.device)

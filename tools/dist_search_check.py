@@ -35,7 +35,7 @@ res = {"rank": rank, "world": world, "offsets_ok": ok}
 for k in (100, 1000):
     Df, If = full.search(q, k)
     for mode, thr in (("all_gather", 1 << 62), ("all_to_all", 0)):
-        store.A2A_MIN_ENTRIES = thr
+        store.A2A_MIN_ENTRIES, store.A2A_MIN_WORLD = thr, 2
         D, I = store.search(q, k)
         same = bool(torch.equal(I, If) and torch.equal(D, Df))
         res[f"k{k}_{mode}"] = same
