@@ -340,3 +340,43 @@ def test_randomised_shapes_against_oracle():
             _check_parity(D, I, Dr, Ir, k, n, scale=np.sqrt(float(d)))
         except AssertionError as e:
             raise AssertionError(f"case nq={nq} n={n} k={k} seg_rows={seg_rows} d={d}: {e}") from e
+
+
+def _aniso(rng, n, d=768):
+    """SURVEY §8d 'aniso' (precision stress, BERT-like): x = mu + s * z, |mu| = 8, per-dimension
+    scale log-uniform in [0.25, 4]."""
+    mu = np.random.default_rng(7).standard_normal(d).astype(np.float32)
+    mu *= 8.0 / np.linalg.norm(mu)
+    s = np.exp(np.random.default_rng(8).uniform(np.log(0.25), np.log(4.0), size=d)).astype(np.float32)
+    return (mu[None, :] + s[None, :] * rng.standard_normal((n, d), dtype=np.float32)).astype(np.float32)
+
+
+@pytest.mark.parametrize("k", [10, 100, 500])
+def test_anisotropic_embeddings_with_common_offset(k):
+    """BERT-like geometry: a large common mean component and a 16x spread of per-dimension
+    scales make the bf16 error large relative to the score gaps; results must stay exact."""
+    rng = np.random.default_rng(31 + k)
+    x = _aniso(rng, 120000)
+    q = _aniso(rng, 256)
+    index = _mk(seg_rows=1 << 15)
+    index.add(x)
+    D, I = index.search(q, k)
+    st = index.search_stats()
+    assert st["flagged_queries"] == 0
+    Dr, Ir = flat_ip.flat_ip_search(x, q, k)
+    scale = float(np.abs(Dr).max())
+    _check_parity(D, I, Dr, Ir, k, 120000, scale=scale * 1e-2)
+
+
+def test_unit_norm_small_magnitude_embeddings():
+    """Cosine-style retrieval: rows normalised to unit length (elements ~0.036)."""
+    rng = np.random.default_rng(77)
+    x = rng.standard_normal((80000, 768), dtype=np.float32)
+    x /= np.linalg.norm(x, axis=1, keepdims=True)
+    q = rng.standard_normal((200, 768), dtype=np.float32)
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    index = _mk(seg_rows=1 << 15)
+    index.add(x)
+    D, I = index.search(q, 100)
+    Dr, Ir = flat_ip.flat_ip_search(x, q, 100)
+    _check_parity(D, I, Dr, Ir, 100, 80000, scale=1e-2)
