@@ -740,8 +740,37 @@ void launch_sgemm(const drt::GemmOperand& A, const drt::GemmOperand& Bm, long lo
     dim3 grid((unsigned)((N + Cfg::BN - 1) / Cfg::BN), (unsigned)((M + Cfg::BM - 1) / Cfg::BM));
     drt::sgemm_kernel<Cfg><<<grid, Cfg::THREADS, 0, st>>>(A, Bm, M, N, K, C, vecA, vecB);
 }
-inline bool use_large_tiles(long long M, long long N, int sm_count) {
-    return ((M + 63) / 64) * ((N + 63) / 64) >= 2ll * sm_count;
+// Tile tier for an M x N output: the largest tile that still gives every SM ~2 CTAs
+// (0 = 32x32, 1 = 64x64, 2 = 128x128 with 8x8 register tiles for FMA-bound problems).
+inline int gemm_tier(long long M, long long N, int sm_count) {
+    if (((M + 127) / 128) * ((N + 127) / 128) >= 2ll * sm_count) return 2;
+    if (((M + 63) / 64) * ((N + 63) / 64) >= 2ll * sm_count) return 1;
+    return 0;
+}
+void launch_sgemm_tiered(const drt::GemmOperand& A, const drt::GemmOperand& Bm, long long M, long long N, long long K,
+                         float* C, cudaStream_t st) {
+    switch (gemm_tier(M, N, 148)) {
+        case 2: launch_sgemm<drt::GemmHuge>(A, Bm, M, N, K, C, st); break;
+        case 1: launch_sgemm<drt::GemmLarge>(A, Bm, M, N, K, C, st); break;
+        default: launch_sgemm<drt::GemmSmall>(A, Bm, M, N, K, C, st); break;
+    }
+}
+template <class C>
+void launch_ce_fwd(const float* x, const float* y, long long B, long long P, int dim, const long long* target,
+                   float loss_scale, float* logits_out, CeWorkspace& w, float* lse_out, float* loss_rows, float* loss_out,
+                   int vec_ok, cudaStream_t st) {
+    dim3 grid((unsigned)((P + C::BN - 1) / C::BN), (unsigned)((B + C::BM - 1) / C::BM));
+    drt::inbatch_ce_fwd_kernel<C><<<grid, C::THREADS, 0, st>>>(
+        x, y, B, P, dim, target, P / B, loss_scale, logits_out, (float*)w.part_max.p, (float*)w.part_sum.p,
+        (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows, loss_out, vec_ok);
+}
+template <class C>
+void launch_ce_dlogits(const float* x, const float* y, long long B, long long P, int dim, const long long* target,
+                       const float* lse, const float* grad_rows, int grad_stride, float grad_scale, float* work, int vec_ok,
+                       cudaStream_t st) {
+    dim3 grid((unsigned)((P + C::BN - 1) / C::BN), (unsigned)((B + C::BM - 1) / C::BM));
+    drt::inbatch_ce_dlogits_kernel<C><<<grid, C::THREADS, 0, st>>>(x, y, B, P, dim, target, P / B, lse, grad_rows, grad_stride,
+                                                                   grad_scale, work, vec_ok);
 }
 }  // namespace
 }  // extern "C++"
@@ -758,25 +787,19 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
     cudaStream_t st = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lk(g_ce_mu);
     CeWorkspace& w = g_ce_ws[device];
-    const bool large = use_large_tiles(B, P, 148);
-    const int bm = large ? drt::GemmLarge::BM : drt::GemmSmall::BM, bn = large ? drt::GemmLarge::BN : drt::GemmSmall::BN;
-    const int ncol = (int)((P + bn - 1) / bn), nrow = (int)((B + bm - 1) / bm);
+    const int tier = gemm_tier(B, P, 148);
+    const int bn = tier == 2 ? drt::GemmHuge::BN : tier == 1 ? drt::GemmLarge::BN : drt::GemmSmall::BN;
+    const int ncol = (int)((P + bn - 1) / bn);
     if ((rc = w.part_max.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
     if ((rc = w.part_sum.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
     if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
     if ((rc = w.ticket.ensure(64)) != DRT_OK) return rc;
     if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, 64, st)); w.ticket_init = true; }
     const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
-    if (large)
-        drt::inbatch_ce_fwd_kernel<drt::GemmLarge><<<dim3(ncol, nrow), drt::GemmLarge::THREADS, 0, st>>>(
-            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), loss_scale, logits_out,
-            (float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows,
-            loss_out, vec_ok);
-    else
-        drt::inbatch_ce_fwd_kernel<drt::GemmSmall><<<dim3(ncol, nrow), drt::GemmSmall::THREADS, 0, st>>>(
-            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), loss_scale, logits_out,
-            (float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, (unsigned int*)w.ticket.p, lse_out, loss_rows,
-            loss_out, vec_ok);
+    const long long* tg = (const long long*)target;
+    if (tier == 2) launch_ce_fwd<drt::GemmHuge>(x, y, B, P, dim, tg, loss_scale, logits_out, w, lse_out, loss_rows, loss_out, vec_ok, st);
+    else if (tier == 1) launch_ce_fwd<drt::GemmLarge>(x, y, B, P, dim, tg, loss_scale, logits_out, w, lse_out, loss_rows, loss_out, vec_ok, st);
+    else launch_ce_fwd<drt::GemmSmall>(x, y, B, P, dim, tg, loss_scale, logits_out, w, lse_out, loss_rows, loss_out, vec_ok, st);
     CUDA_TRY(cudaGetLastError());
     return DRT_OK;
 }
@@ -792,27 +815,15 @@ int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
-    if (use_large_tiles(B, P, 148)) {
-        using C = drt::GemmLarge;
-        drt::inbatch_ce_dlogits_kernel<C><<<dim3((unsigned)((P + C::BN - 1) / C::BN), (unsigned)((B + C::BM - 1) / C::BM)), C::THREADS, 0, st>>>(
-            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), lse, grad_rows, grad_stride, grad_scale, work, vec_ok);
-    } else {
-        using C = drt::GemmSmall;
-        drt::inbatch_ce_dlogits_kernel<C><<<dim3((unsigned)((P + C::BN - 1) / C::BN), (unsigned)((B + C::BM - 1) / C::BM)), C::THREADS, 0, st>>>(
-            x, y, (long long)B, (long long)P, dim, (const long long*)target, (long long)(P / B), lse, grad_rows, grad_stride, grad_scale, work, vec_ok);
-    }
+    const long long* tg = (const long long*)target;
+    const int tier = gemm_tier(B, P, 148);
+    if (tier == 2) launch_ce_dlogits<drt::GemmHuge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
+    else if (tier == 1) launch_ce_dlogits<drt::GemmLarge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
+    else launch_ce_dlogits<drt::GemmSmall>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     // dx[B,d] = dlogits[B,P] · y[P,d]   (A k-contiguous, B n-contiguous)
-    if (dx) {
-        const drt::GemmOperand A{work, (long long)P, 1}, Bm{y, 1, (long long)dim};
-        if (use_large_tiles(B, dim, 148)) launch_sgemm<drt::GemmLarge>(A, Bm, B, dim, P, dx, st);
-        else launch_sgemm<drt::GemmSmall>(A, Bm, B, dim, P, dx, st);
-    }
+    if (dx) launch_sgemm_tiered(drt::GemmOperand{work, (long long)P, 1}, drt::GemmOperand{y, 1, (long long)dim}, B, dim, P, dx, st);
     // dy[P,d] = dlogitsᵀ[P,B] · x[B,d]  (A m-contiguous, B n-contiguous)
-    if (dy) {
-        const drt::GemmOperand A{work, 1, (long long)P}, Bm{x, 1, (long long)dim};
-        if (use_large_tiles(P, dim, 148)) launch_sgemm<drt::GemmLarge>(A, Bm, P, dim, B, dy, st);
-        else launch_sgemm<drt::GemmSmall>(A, Bm, P, dim, B, dy, st);
-    }
+    if (dy) launch_sgemm_tiered(drt::GemmOperand{work, 1, (long long)P}, drt::GemmOperand{x, 1, (long long)dim}, P, dim, B, dy, st);
     CUDA_TRY(cudaGetLastError());
     return DRT_OK;
 }

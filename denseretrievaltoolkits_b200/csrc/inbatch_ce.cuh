@@ -42,6 +42,7 @@ struct GemmCfg {
 };
 using GemmSmall = GemmCfg<32, 32, 4, 2, 64>;    // 128 threads, 36 KB smem
 using GemmLarge = GemmCfg<64, 64, 4, 4, 32>;    // 256 threads, 34 KB smem
+using GemmHuge = GemmCfg<128, 128, 8, 8, 16>;   // 256 threads, 34 KB smem: 64 FMAs per 4 LDS.128
 
 // Vector v (of NV per thread) of a [ROWS x BK] operand tile.  Element (r, k) lives at
 // p[(r0 + r) * s_outer + (k0 + k) * s_k]; out-of-range -> 0.  fetch issues the global load into
@@ -131,11 +132,17 @@ __device__ __forceinline__ void gemm_tile(const GemmOperand& A, const GemmOperan
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             float a[TM], b[TN];
-            const float4 a4 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * TM]);
-            a[0] = a4.x; a[1] = a4.y; a[2] = a4.z; a[3] = a4.w;
-            if constexpr (TN == 4) {
-                const float4 b4 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * TN]);
-                b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
+#pragma unroll
+            for (int v = 0; v < TM / 4; ++v) {
+                const float4 a4 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * TM + 4 * v]);
+                a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
+            }
+            if constexpr (TN % 4 == 0) {
+#pragma unroll
+                for (int v = 0; v < TN / 4; ++v) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * TN + 4 * v]);
+                    b[4 * v] = b4.x; b[4 * v + 1] = b4.y; b[4 * v + 2] = b4.z; b[4 * v + 3] = b4.w;
+                }
             } else {
                 const float2 b2 = *reinterpret_cast<const float2*>(&sb[buf][kk][tx * TN]);
                 b[0] = b2.x; b[1] = b2.y;

@@ -182,6 +182,13 @@ class ShardedCorpusStore:
             dist.all_gather_into_tensor(oD, mD.contiguous(), group=self.group)
             dist.all_gather_into_tensor(oI, mI.contiguous(), group=self.group)
             return oD[:Q], oI[:Q]
+        if D.is_cuda:
+            # gather straight into the [W, Q, k] layout the merge kernel reads (no list copies)
+            gD = torch.empty((W * Q, k), dtype=D.dtype, device=D.device)
+            gI = torch.empty((W * Q, k), dtype=I.dtype, device=I.device)
+            dist.all_gather_into_tensor(gD, D.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(gI, I.contiguous(), group=self.group)
+            return self._merge(gD.view(W, Q, k), gI.view(W, Q, k), k)
         Ds = [torch.empty_like(D) for _ in range(W)]
         Is = [torch.empty_like(I) for _ in range(W)]
         dist.all_gather(Ds, D, group=self.group)
