@@ -97,8 +97,8 @@ def load() -> ctypes.CDLL:
                                        c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]
     lib.drt_inbatch_ce_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
-                                       c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p,
-                                       c_void_p, c_int, c_void_p]
+                                       c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
+                                       c_void_p, c_void_p, c_int, c_void_p]
     lib.drt_filter_negatives.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                                          c_void_p, c_int, c_void_p]
     for name in SYMBOLS:

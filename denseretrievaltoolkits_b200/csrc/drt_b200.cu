@@ -740,11 +740,11 @@ void launch_sgemm(const drt::GemmOperand& A, const drt::GemmOperand& Bm, long lo
     dim3 grid((unsigned)((N + Cfg::BN - 1) / Cfg::BN), (unsigned)((M + Cfg::BM - 1) / Cfg::BM));
     drt::sgemm_kernel<Cfg><<<grid, Cfg::THREADS, 0, st>>>(A, Bm, M, N, K, C, vecA, vecB);
 }
-// Tile tier for an M x N output: the largest tile that still gives every SM ~2 CTAs
+// Tile tier for an M x N output: the largest tile that still gives every SM a CTA
 // (0 = 32x32, 1 = 64x64, 2 = 128x128 with 8x8 register tiles for FMA-bound problems).
 inline int gemm_tier(long long M, long long N, int sm_count) {
-    if (((M + 127) / 128) * ((N + 127) / 128) >= 2ll * sm_count) return 2;
-    if (((M + 63) / 64) * ((N + 63) / 64) >= 2ll * sm_count) return 1;
+    if (((M + 127) / 128) * ((N + 127) / 128) >= 1ll * sm_count) return 2;
+    if (((M + 63) / 64) * ((N + 63) / 64) >= 1ll * sm_count) return 1;
     return 0;
 }
 void launch_sgemm_tiered(const drt::GemmOperand& A, const drt::GemmOperand& Bm, long long M, long long N, long long K,
@@ -805,8 +805,8 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
 }
 
 int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim, const int64_t* target,
-                       const float* lse, const float* grad_rows, int grad_stride, float grad_scale, float* work,
-                       float* dx, float* dy, int device, void* stream) {
+                       const float* lse, const float* logits, const float* grad_rows, int grad_stride, float grad_scale,
+                       float* work, float* dx, float* dy, int device, void* stream) {
     if (B <= 0 || P <= 0 || dim <= 0) return fail(DRT_E_INVALID, "bad shape");
     if (!x || !y || !lse || !grad_rows || !work) return fail(DRT_E_INVALID, "NULL pointer");
     if (grad_stride != 0 && grad_stride != 1) return fail(DRT_E_INVALID, "grad_stride must be 0 (scalar) or 1 (per row)");
@@ -817,7 +817,12 @@ int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int
     const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
     const long long* tg = (const long long*)target;
     const int tier = gemm_tier(B, P, 148);
-    if (tier == 2) launch_ce_dlogits<drt::GemmHuge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
+    if (logits) {    // forward kept the logits: dlogits is one elementwise pass (in place when work == logits)
+        const long long total = (long long)B * P;
+        const int blocks = (int)std::min<long long>((total + 255) / 256, 148ll * 16);
+        drt::ce_dlogits_from_logits_kernel<<<blocks, 256, 0, st>>>(logits, (long long)B, (long long)P, tg, (long long)(P / B), lse,
+                                                                  grad_rows, grad_stride, grad_scale, work);
+    } else if (tier == 2) launch_ce_dlogits<drt::GemmHuge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     else if (tier == 1) launch_ce_dlogits<drt::GemmLarge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     else launch_ce_dlogits<drt::GemmSmall>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     // dx[B,d] = dlogits[B,P] · y[P,d]   (A k-contiguous, B n-contiguous)

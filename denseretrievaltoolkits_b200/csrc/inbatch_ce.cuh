@@ -39,6 +39,16 @@ struct GemmCfg {
     static constexpr int PAD = 4;
     static constexpr int VA = BM * BK / 4 / THREADS, VB = BN * BK / 4 / THREADS;   // float4 per thread per slab
     static_assert(VA * 4 * THREADS == BM * BK && VB * 4 * THREADS == BN * BK, "slab must split into whole float4s");
+    // Tile-local row / column of the thread's i-th / j-th output.  With 8-wide register tiles the
+    // eight outputs are two groups of four, BM/2 (BN/2) apart, so that the lanes of a quarter
+    // warp read CONSECUTIVE float4s of the smem fragment (a contiguous 8-float strip per lane
+    // would make every LDS.128 a 2-way bank conflict).
+    __host__ __device__ static constexpr int row_of(int ty, int i) {
+        return TM == 8 ? (i >> 2) * (BM / 2) + ty * 4 + (i & 3) : ty * TM + i;
+    }
+    __host__ __device__ static constexpr int col_of(int tx, int j) {
+        return TN == 8 ? (j >> 2) * (BN / 2) + tx * 4 + (j & 3) : tx * TN + j;
+    }
 };
 using GemmSmall = GemmCfg<32, 32, 4, 2, 64>;    // 128 threads, 36 KB smem
 using GemmLarge = GemmCfg<64, 64, 4, 4, 32>;    // 256 threads, 34 KB smem
@@ -134,13 +144,13 @@ __device__ __forceinline__ void gemm_tile(const GemmOperand& A, const GemmOperan
             float a[TM], b[TN];
 #pragma unroll
             for (int v = 0; v < TM / 4; ++v) {
-                const float4 a4 = *reinterpret_cast<const float4*>(&sa[buf][kk][ty * TM + 4 * v]);
+                const float4 a4 = *reinterpret_cast<const float4*>(&sa[buf][kk][Cfg::row_of(ty, 4 * v)]);
                 a[4 * v] = a4.x; a[4 * v + 1] = a4.y; a[4 * v + 2] = a4.z; a[4 * v + 3] = a4.w;
             }
             if constexpr (TN % 4 == 0) {
 #pragma unroll
                 for (int v = 0; v < TN / 4; ++v) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(&sb[buf][kk][tx * TN + 4 * v]);
+                    const float4 b4 = *reinterpret_cast<const float4*>(&sb[buf][kk][Cfg::col_of(tx, 4 * v)]);
                     b[4 * v] = b4.x; b[4 * v + 1] = b4.y; b[4 * v + 2] = b4.z; b[4 * v + 3] = b4.w;
                 }
             } else {
@@ -184,12 +194,12 @@ inbatch_ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, 
     const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const long long row = m0 + ty * TM + i;
+        const long long row = m0 + Cfg::row_of(ty, i);
         const long long tcol = (row < B) ? (target ? target[row] : row * target_stride) : -1;
         float mx = -FLT_MAX;
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const long long col = n0 + tx * TN + j;
+            const long long col = n0 + Cfg::col_of(tx, j);
             if (row < B && col < P) {
                 if (logits_out) logits_out[row * P + col] = acc[i][j];
                 if (col == tcol) tgt_logit[row] = acc[i][j];
@@ -202,7 +212,7 @@ inbatch_ce_fwd_kernel(const float* __restrict__ x, const float* __restrict__ y, 
         float se = 0.f;
 #pragma unroll
         for (int j = 0; j < TN; ++j)
-            if (row < B && n0 + tx * TN + j < P) se += expf(acc[i][j] - mx);
+            if (row < B && n0 + Cfg::col_of(tx, j) < P) se += expf(acc[i][j] - mx);
 #pragma unroll
         for (int o = Cfg::TX / 2; o > 0; o >>= 1) se += __shfl_xor_sync(0xffffffffu, se, o);
         if (tx == 0 && row < B) {
@@ -281,15 +291,30 @@ inbatch_ce_dlogits_kernel(const float* __restrict__ x, const float* __restrict__
     const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const long long row = m0 + ty * TM + i;
+        const long long row = m0 + Cfg::row_of(ty, i);
         if (row >= B) continue;
         const long long tcol = target ? target[row] : row * target_stride;
         const float l = lse[row], g = grad_scale * grad_rows[row * grad_stride];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const long long col = n0 + tx * TN + j;
+            const long long col = n0 + Cfg::col_of(tx, j);
             if (col < P) dlogits[row * P + col] = g * (expf(acc[i][j] - l) - (col == tcol ? 1.f : 0.f));
         }
+    }
+}
+
+// Backward step 1, when the forward kept its logits: one elementwise pass.
+__global__ void ce_dlogits_from_logits_kernel(const float* logits, long long B, long long P,
+                                              const long long* __restrict__ target, long long target_stride,
+                                              const float* __restrict__ lse, const float* __restrict__ grad_rows,
+                                              int grad_stride, float grad_scale, float* dlogits) {
+    const long long total = B * P;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const long long row = i / P, col = i - row * P;
+        const long long tcol = target ? target[row] : row * target_stride;
+        const float g = grad_scale * grad_rows[row * grad_stride];
+        dlogits[i] = g * (expf(logits[i] - lse[row]) - (col == tcol ? 1.f : 0.f));
     }
 }
 
@@ -308,7 +333,7 @@ sgemm_kernel(GemmOperand A, GemmOperand Bm, long long M, long long N, long long 
     for (int i = 0; i < TM; ++i)
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const long long m = m0 + ty * TM + i, n = n0 + tx * TN + j;
+            const long long m = m0 + Cfg::row_of(ty, i), n = n0 + Cfg::col_of(tx, j);
             if (m < M && n < N) C[m * N + n] = acc[i][j];
         }
 }

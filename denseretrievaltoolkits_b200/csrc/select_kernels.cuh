@@ -241,12 +241,12 @@ exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __re
     const int tx = threadIdx.x % Cfg::TX, ty = threadIdx.x / Cfg::TX;
 #pragma unroll
     for (int i = 0; i < TM; ++i) {
-        const long long qi = m0 + ty * TM + i;
+        const long long qi = m0 + Cfg::row_of(ty, i);
         if (qi >= nq) continue;
         const float t = thr[qi];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
-            const long long col = n0 + tx * TN + j;
+            const long long col = n0 + Cfg::col_of(tx, j);
             if (col < nrows && acc[i][j] > t) {
                 const uint32_t slot = atomicAdd(cnt + qi, 1u);
                 if (slot < cap) cand[static_cast<size_t>(qi) * cap + slot] = pack_key(acc[i][j], row_id0 + static_cast<uint32_t>(col));

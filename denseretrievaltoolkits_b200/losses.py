@@ -18,6 +18,7 @@ from torch import distributed as dist
 from . import _lib
 
 _REDUCTIONS = ("mean", "sum", "none")
+_KEEP_LOGITS_BYTES = 1 << 30
 
 
 def _f32c(t: Tensor) -> Tensor:
@@ -49,7 +50,10 @@ class _InBatchCE(torch.autograd.Function):
             tgt = target.detach()
             if tgt.dtype is not torch.int64 or tgt.device != dev or not tgt.is_contiguous():
                 tgt = tgt.to(device=dev, dtype=torch.int64).contiguous()
-        logits = torch.empty((B, P), dtype=torch.float32, device=dev) if want_logits else None
+        # the logits are kept for the backward (one elementwise pass instead of a second GEMM)
+        # unless the matrix is huge; they are only RETURNED when the caller asked for them
+        keep_logits = want_logits or (B * P * 4 <= _KEEP_LOGITS_BYTES and any(ctx.needs_input_grad[:2]))
+        logits = torch.empty((B, P), dtype=torch.float32, device=dev) if keep_logits else None
         lse = torch.empty((B,), dtype=torch.float32, device=dev)           # saved for backward
         out = torch.empty((B + 1,), dtype=torch.float32, device=dev)       # per-row loss | total
         scale = 1.0 / B if reduction == "mean" else 1.0
@@ -59,33 +63,35 @@ class _InBatchCE(torch.autograd.Function):
             xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if tgt is not None else None, scale,
             logits.data_ptr() if logits is not None else None, lse.data_ptr(), base, base + 4 * B,
             dev.index, stream), "inbatch_ce_fwd")
-        ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else lse)
+        ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else lse, logits if logits is not None else lse)
         ctx.has_target = tgt is not None
+        ctx.has_logits = logits is not None
+        ctx.logits_private = logits is not None and not want_logits      # may be overwritten in place
         ctx.reduction = reduction
         ctx.scale = scale
         ctx.in_dtypes = (x.dtype, y.dtype)
-        if logits is None:
-            logits = out.new_empty(0)
-        ctx.mark_non_differentiable(logits)
+        ret_logits = logits if want_logits else out.new_empty(0)
+        ctx.mark_non_differentiable(ret_logits)
         loss = out[:B] if reduction == "none" else out[B]
-        return loss, logits
+        return loss, ret_logits
 
     @staticmethod
     def backward(ctx, grad_loss: Tensor, _grad_logits):
-        xc, yc, lse, tgt = ctx.saved_tensors
+        xc, yc, lse, tgt, logits = ctx.saved_tensors
         lib = _lib.load()
         B, d = xc.shape
         P = yc.shape[0]
         dev = xc.device
         g = _f32c(grad_loss)
         per_row = ctx.reduction == "none"
-        work = torch.empty((B, P), dtype=torch.float32, device=dev)
+        work = logits if ctx.logits_private else torch.empty((B, P), dtype=torch.float32, device=dev)
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = torch.empty_like(xc) if need_x else None
         dy = torch.empty_like(yc) if need_y else None
         _lib.check(lib.drt_inbatch_ce_bwd(
             xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if ctx.has_target else None,
-            lse.data_ptr(), g.data_ptr(), 1 if per_row else 0, ctx.scale, work.data_ptr(),
+            lse.data_ptr(), logits.data_ptr() if ctx.has_logits else None, g.data_ptr(), 1 if per_row else 0, ctx.scale,
+            work.data_ptr(),
             dx.data_ptr() if dx is not None else None, dy.data_ptr() if dy is not None else None,
             dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_bwd")
         if dx is not None and ctx.in_dtypes[0] is not torch.float32:
@@ -158,7 +164,7 @@ class _ShardedInBatchCE(torch.autograd.Function):
         dx = torch.empty_like(xc)
         dy_all = torch.empty_like(y_all)
         _lib.check(lib.drt_inbatch_ce_bwd(xc.data_ptr(), y_all.data_ptr(), B, world * P, d, target.data_ptr(), lse.data_ptr(),
-                                          g.data_ptr(), 0, coef, work.data_ptr(), dx.data_ptr(), dy_all.data_ptr(),
+                                          None, g.data_ptr(), 0, coef, work.data_ptr(), dx.data_ptr(), dy_all.data_ptr(),
                                           dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_bwd")
         dy = torch.empty((P, d), dtype=torch.float32, device=dev)
         dist.reduce_scatter_tensor(dy, dy_all, group=group)

@@ -134,11 +134,13 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
  * g_i = grad_scale * grad_rows[i * grad_stride]: grad_stride = 1 for a per-row upstream gradient
  * (reduction='none'), 0 when grad_rows points at ONE device float (reduction='mean'/'sum': the
  * scalar upstream gradient, grad_scale = 1/B or 1).  dx = dlogits·y, dy = dlogitsᵀ·x.  `work` is
- * a device scratch of B*P floats (holds dlogits).  dx / dy may be NULL to skip that gradient. */
+ * a device scratch of B*P floats (holds dlogits).  `logits` = the forward's logits_out if it was
+ * kept (dlogits is then one elementwise pass; `work` may alias it), or NULL to recompute the
+ * logits tile by tile.  dx / dy may be NULL to skip that gradient. */
 int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim,
-                       const int64_t* target, const float* lse, const float* grad_rows,
-                       int grad_stride, float grad_scale, float* work, float* dx, float* dy,
-                       int device, void* stream);
+                       const int64_t* target, const float* lse, const float* logits,
+                       const float* grad_rows, int grad_stride, float grad_scale, float* work,
+                       float* dx, float* dy, int device, void* stream);
 
 /* ---- mining filter -------------------------------------------------------------------------
  * process_sample (DRT/trainer/sampler.py:69-80): walk each query's retrieved ids in rank order,
