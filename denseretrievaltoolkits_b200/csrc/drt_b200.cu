@@ -17,6 +17,7 @@
 #include "../../include/drt_b200.h"
 #include "inbatch_ce.cuh"
 #include "mips_filter.cuh"
+#include "gemm_tc.cuh"
 #include "select_kernels.cuh"
 
 namespace {
@@ -714,7 +715,14 @@ int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t
 
 // ---- in-batch CE ----------------------------------------------------------------------------
 namespace {
-struct CeWorkspace { DevBuf part_max, part_sum, tgt, ticket; bool ticket_init = false; };
+struct CeWorkspace {
+    DevBuf part_max, part_sum, tgt, ticket;
+    DevBuf a_split, b_split, partials, logits;   // tensor-core path: bf16x3 operands, split-K partials
+    bool ticket_init = false;
+    int* err_host = nullptr;
+    int* err_dev = nullptr;
+    bool tc_attrs = false;
+};
 std::mutex g_ce_mu;
 std::map<int, CeWorkspace> g_ce_ws;
 }  // namespace
@@ -772,6 +780,85 @@ void launch_ce_dlogits(const float* x, const float* y, long long B, long long P,
     drt::inbatch_ce_dlogits_kernel<C><<<grid, C::THREADS, 0, st>>>(x, y, B, P, dim, target, P / B, lse, grad_rows, grad_stride,
                                                                    grad_scale, work, vec_ok);
 }
+
+// ---- tensor-core (bf16x3 split) GEMM for the large loss shapes ------------------------------
+__global__ void sum_partials_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ C) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int s = 0; s < S; ++s) a += part[(long long)s * n + i];
+        C[i] = a;
+    }
+}
+
+inline bool tc_shape_ok(long long M, long long N, long long K) {
+    // worth the split + launch overhead only for big problems; K' = 6K must be a multiple of 64
+    return K % 32 == 0 && (double)M * (double)N * (double)K >= 2.0e9 && M >= 128 && N >= 256;
+}
+
+int ce_tc_setup(CeWorkspace& w) {
+    if (!w.tc_attrs) {
+        CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::GemmTcCfg<1>::kSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::GemmTcCfg<2>::kSmemBytes));
+        if (cudaHostAlloc((void**)&w.err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+            cudaHostGetDevicePointer((void**)&w.err_dev, w.err_host, 0) != cudaSuccess) {
+            (void)cudaGetLastError();
+            return fail(DRT_E_CUDA, "pinned host allocation failed");
+        }
+        *w.err_host = 0;
+        w.tc_attrs = true;
+    }
+    return DRT_OK;
+}
+
+// C[M,N] = A'[M,Kp] · B'[N,Kp]^T, A'/B' bf16 K-major (Kp = 6K, multiple of 64).  Split-K over
+// `ksplit` chunks when the output has too few tiles to fill the GPU; partials are summed.
+int gemm_tc_nt(CeWorkspace& w, const void* a_split, const void* b_split, long long M, long long N, long long Kp,
+               float* C, cudaStream_t st) {
+    int rc = ce_tc_setup(w);
+    if (rc != DRT_OK) return rc;
+    const int kctas = M > drt::kTileM ? 2 : 1;
+    const int clusters_max = 148 / kctas;
+    const int m_tiles = (int)((M + drt::kTileM * kctas - 1) / (drt::kTileM * kctas));
+    const int n_tiles = (int)((N + drt::kTileN - 1) / drt::kTileN);
+    const int nkb = (int)(Kp / drt::kBlockK);
+    int ksplit = 1;
+    if (m_tiles * n_tiles < clusters_max) ksplit = std::max(1, std::min(nkb / 16, (2 * clusters_max + m_tiles * n_tiles - 1) / (m_tiles * n_tiles)));
+    CUtensorMap ta, tb;
+    if ((rc = make_tmap_bf16(&ta, a_split, (uint64_t)M, (uint64_t)Kp, drt::kTileM)) != DRT_OK) return rc;
+    if ((rc = make_tmap_bf16(&tb, b_split, (uint64_t)N, (uint64_t)Kp, drt::kTileN / kctas)) != DRT_OK) return rc;
+    float* out = C;
+    if (ksplit > 1) {
+        if ((rc = w.partials.ensure((size_t)ksplit * M * N * 4)) != DRT_OK) return rc;
+        out = (float*)w.partials.p;
+    }
+    {
+        drt::GemmTcParams p;
+        p.num_m_tiles = m_tiles; p.num_n_tiles = n_tiles; p.unit_tiles = 1;
+        p.ksplit = ksplit; p.num_k_blocks = nkb;
+        p.M = M; p.N = N; p.ldc = N; p.C = out; p.err = w.err_dev;
+        const int total = m_tiles * n_tiles * ksplit;
+        const int clusters = std::max(1, std::min(clusters_max, total));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(clusters * kctas);
+        cfg.blockDim = dim3(drt::kFilterThreads);
+        cfg.dynamicSmemBytes = kctas == 2 ? drt::GemmTcCfg<2>::kSmemBytes : drt::GemmTcCfg<1>::kSmemBytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kctas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (kctas == 2) CUDA_TRY(cudaLaunchKernelEx(&cfg, drt::gemm_tc_nt_kernel<2>, ta, tb, p));
+        else CUDA_TRY(cudaLaunchKernelEx(&cfg, drt::gemm_tc_nt_kernel<1>, ta, tb, p));
+    }
+    if (ksplit > 1) {
+        const long long n = M * N;
+        sum_partials_kernel<<<(int)std::min<long long>((n + 255) / 256, 148 * 8), 256, 0, st>>>((const float*)w.partials.p, ksplit, n, C);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return DRT_OK;
+}
+
+inline int split_blocks(long long total) { return (int)std::min<long long>((total + 255) / 256, 148ll * 16); }
 }  // namespace
 }  // extern "C++"
 
@@ -787,6 +874,22 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
     cudaStream_t st = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lk(g_ce_mu);
     CeWorkspace& w = g_ce_ws[device];
+    if (tc_shape_ok(B, P, dim) && !getenv("DRT_B200_CE_SIMT")) {
+        // large shape: fp32-accurate logits on the tensor cores (bf16x3 split), then row-wise CE
+        float* lg = logits_out;
+        if (!lg) { if ((rc = w.logits.ensure((size_t)B * P * 4)) != DRT_OK) return rc; lg = (float*)w.logits.p; }
+        if ((rc = w.a_split.ensure((size_t)B * 6 * dim * 2)) != DRT_OK) return rc;
+        if ((rc = w.b_split.ensure((size_t)P * 6 * dim * 2)) != DRT_OK) return rc;
+        if ((rc = w.ticket.ensure(64)) != DRT_OK) return rc;
+        if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, 64, st)); w.ticket_init = true; }
+        drt::split3_rows_kernel<<<split_blocks(B * dim), 256, 0, st>>>(x, B, dim, dim, (__nv_bfloat16*)w.a_split.p, 0);
+        drt::split3_rows_kernel<<<split_blocks(P * dim), 256, 0, st>>>(y, P, dim, dim, (__nv_bfloat16*)w.b_split.p, 1);
+        if ((rc = gemm_tc_nt(w, w.a_split.p, w.b_split.p, B, P, 6ll * dim, lg, st)) != DRT_OK) return rc;
+        drt::ce_rows_from_logits_kernel<<<(unsigned)B, 256, 0, st>>>(lg, B, P, (const long long*)target, (long long)(P / B), loss_scale,
+                                                                   lse_out, loss_rows, loss_out, (unsigned int*)w.ticket.p);
+        CUDA_TRY(cudaGetLastError());
+        return DRT_OK;
+    }
     const int tier = gemm_tier(B, P, 148);
     const int bn = tier == 2 ? drt::GemmHuge::BN : tier == 1 ? drt::GemmLarge::BN : drt::GemmSmall::BN;
     const int ncol = (int)((P + bn - 1) / bn);
@@ -825,6 +928,31 @@ int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int
     } else if (tier == 2) launch_ce_dlogits<drt::GemmHuge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     else if (tier == 1) launch_ce_dlogits<drt::GemmLarge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     else launch_ce_dlogits<drt::GemmSmall>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
+    const bool tc = !getenv("DRT_B200_CE_SIMT") && tc_shape_ok(B, dim, P) && tc_shape_ok(P, dim, B) && dim >= 256;
+    if (tc) {
+        std::lock_guard<std::mutex> lk(g_ce_mu);
+        CeWorkspace& w = g_ce_ws[device];
+        const size_t need = (size_t)std::max(B, P) * 6 * std::max<long long>(std::max(B, P), dim) * 2;
+        if ((rc = w.a_split.ensure((size_t)B * 6 * P * 2)) != DRT_OK) return rc;      // dL' / dLT' : B*6P == P*6B elements
+        if ((rc = w.b_split.ensure((size_t)dim * 6 * std::max(B, P) * 2)) != DRT_OK) return rc;
+        (void)need;
+        dim3 tb(32, 8);
+        if (dx) {   // dx[B,d] = dL[B,P] · (yT)[d,P]^T
+            drt::split3_rows_kernel<<<split_blocks(B * P), 256, 0, st>>>(work, B, P, P, (__nv_bfloat16*)w.a_split.p, 0);
+            drt::split3_transpose_kernel<<<dim3((unsigned)((dim + 31) / 32), (unsigned)((P + 31) / 32)), tb, 0, st>>>(
+                y, P, dim, (__nv_bfloat16*)w.b_split.p, 1);
+            if ((rc = gemm_tc_nt(w, w.a_split.p, w.b_split.p, B, dim, 6ll * P, dx, st)) != DRT_OK) return rc;
+        }
+        if (dy) {   // dy[P,d] = (dLT)[P,B] · (xT)[d,B]^T
+            drt::split3_transpose_kernel<<<dim3((unsigned)((P + 31) / 32), (unsigned)((B + 31) / 32)), tb, 0, st>>>(
+                work, B, P, (__nv_bfloat16*)w.a_split.p, 0);
+            drt::split3_transpose_kernel<<<dim3((unsigned)((dim + 31) / 32), (unsigned)((B + 31) / 32)), tb, 0, st>>>(
+                x, B, dim, (__nv_bfloat16*)w.b_split.p, 1);
+            if ((rc = gemm_tc_nt(w, w.a_split.p, w.b_split.p, P, dim, 6ll * B, dy, st)) != DRT_OK) return rc;
+        }
+        CUDA_TRY(cudaGetLastError());
+        return DRT_OK;
+    }
     // dx[B,d] = dlogits[B,P] · y[P,d]   (A k-contiguous, B n-contiguous)
     if (dx) launch_sgemm_tiered(drt::GemmOperand{work, (long long)P, 1}, drt::GemmOperand{y, 1, (long long)dim}, B, dim, P, dx, st);
     // dy[P,d] = dlogitsᵀ[P,B] · x[B,d]  (A m-contiguous, B n-contiguous)
