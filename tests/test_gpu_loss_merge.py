@@ -183,3 +183,38 @@ def test_dense_mining_end_to_end():
     assert (neg.cpu().numpy() == ref).mean() > 0.999
     for r in range(40):
         assert not ((neg[r].cpu().numpy() >= pb[r]) & (neg[r].cpu().numpy() < pe[r])).any()
+
+
+def test_tensor_core_loss_path_is_fp32_accurate(monkeypatch):
+    """Large shapes run the logits / dx / dy contractions on tcgen05 through an exact 3-way bf16
+    split (6 partial products, fp32 accumulation).  Scores must stay within the path's 1e-4
+    relative tolerance — measured ~1e-6 against float64 — and agree with the fp32 SIMT path."""
+    from denseretrievaltoolkits_b200.losses import SimpleContrastiveLoss, inbatch_scores_and_loss
+
+    B, n, d = 1024, 8, 768
+    gen = torch.Generator(device="cuda").manual_seed(4)
+    x = torch.randn((B, d), generator=gen, device="cuda") * 3.0
+    y = torch.randn((B * n, d), generator=gen, device="cuda") * 0.3 + 0.1
+    loss_tc, scores = inbatch_scores_and_loss(x, y, n)
+    ref64 = x.double() @ y.double().t()
+    rel = ((scores.double() - ref64).abs() / ref64.abs().clamp_min(1.0)).max().item()
+    assert rel < 1e-5, rel                                   # bf16 single pass would be ~4e-3 here
+    x1, y1 = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    l1 = SimpleContrastiveLoss()(x1, y1)
+    l1.backward()
+    monkeypatch.setenv("DRT_B200_CE_SIMT", "1")              # same call on the fp32 CUDA-core path
+    x2, y2 = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    l2 = SimpleContrastiveLoss()(x2, y2)
+    l2.backward()
+    monkeypatch.delenv("DRT_B200_CE_SIMT")
+    torch.testing.assert_close(l1, l2, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(loss_tc, l2.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-3, atol=1e-7)
+    torch.testing.assert_close(y1.grad, y2.grad, rtol=1e-3, atol=1e-7)
+    # ragged large shape (M, N not multiples of the 128 / 256 tiles; K multiple of 32)
+    xr, yr = x[:1000].contiguous(), y[:7968].contiguous()
+    lr_, sr = inbatch_scores_and_loss(xr, yr, 7)
+    ref = xr.double() @ yr.double().t()
+    assert ((sr.double() - ref).abs() / ref.abs().clamp_min(1.0)).max().item() < 1e-5
+    tgt = torch.arange(0, 1000 * 7, 7, device="cuda")
+    torch.testing.assert_close(lr_, torch.nn.functional.cross_entropy(ref.float(), tgt), rtol=1e-4, atol=1e-5)
