@@ -8,15 +8,16 @@
 // must match to 1e-4 relative, so the contraction runs as fp32 FFMA (a single bf16 tensor-core
 // pass would put ~5e-4 relative error on the loss).  At the named shape (128 x 1024 x 768,
 // 0.2 GFLOP, 3.5 MB of operands) the step is launch-latency bound, not FLOP bound; the win
-// over the eager path is one launch for scores + log-sum-exp + NLL (and no HBM round trip of
-// the score matrix unless the caller asks for it), and three launches for the backward.
+// over the eager path is one launch for scores + log-sum-exp + NLL + reduction, and three
+// launches for the backward (elementwise dlogits from the kept logits, dx, dy).  Large shapes
+// (B*P*d >= 2e9) take the tcgen05 path in gemm_tc.cuh instead.
 //
 // One register-tiled SIMT GEMM core serves all three contractions:
 //   NT  logits  = x · yᵀ          A(m,k)=x[m*d+k]    B(k,n)=y[n*d+k]
 //   NN  dx      = dlogits · y      A(m,k)=dL[m*P+k]   B(k,n)=y[k*d+n]
 //   TN  dy      = dlogitsᵀ · x     A(m,k)=dL[k*P+m]   B(k,n)=x[k*d+n]
-// with two tile shapes: 32x32 / 128 threads (small problems: enough CTAs to cover 148 SMs) and
-// 64x64 / 256 threads (large problems: 2x less L2 traffic per FLOP).
+// with three tile shapes chosen by how many tiles the output has (every SM should get a CTA):
+// 32x32 / 128 threads, 64x64 / 256 threads, 128x128 / 256 threads with 8x8 register tiles.
 #pragma once
 #include <cfloat>
 #include <cstdint>

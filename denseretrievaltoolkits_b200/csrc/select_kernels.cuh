@@ -40,8 +40,8 @@ __global__ void init_query_state_kernel(float* thr, uint32_t* cnt, int nq) {
     if (i < nq) { thr[i] = -FLT_MAX; cnt[i] = 0u; }   // faiss: heap starts at -FLT_MAX
 }
 
-// K-select: one CTA per query.  If the query gathered more than `keep` candidates, sort them,
-// keep the best `keep` (score desc, row asc) and publish the keep-th score as the new admission
+// K-select: one CTA per query.  If the query gathered more than `keep` candidates, keep the
+// best `keep` (score desc, row asc) and publish the keep-th score as the new admission
 // threshold.  Chunks are visited in ascending row order and admission is strict (>), so a later
 // row that ties the threshold loses to the earlier one — the same outcome as faiss' heap.
 //
