@@ -380,3 +380,19 @@ def test_unit_norm_small_magnitude_embeddings():
     D, I = index.search(q, 100)
     Dr, Ir = flat_ip.flat_ip_search(x, q, 100)
     _check_parity(D, I, Dr, Ir, 100, 80000, scale=1e-2)
+
+
+def test_query_count_above_internal_batch():
+    """More than 16,384 queries in one call are processed in internal batches (bounded workspace);
+    device and host paths must agree with each other and with the oracle."""
+    rng = np.random.default_rng(55)
+    x = rng.standard_normal((6000, 128), dtype=np.float32)
+    q = rng.standard_normal((20001, 128), dtype=np.float32)
+    index = _mk(d=128, seg_rows=2048)
+    index.add(x)
+    D, I = index.search(q, 20)
+    Dd, Id = index.search(torch.from_numpy(q).cuda(), 20)
+    np.testing.assert_array_equal(I, Id.cpu().numpy())
+    np.testing.assert_array_equal(D, Dd.cpu().numpy())
+    Dr, Ir = flat_ip.flat_ip_search(x, q[16000:16800], 20)       # rows straddling the batch boundary
+    _check_parity(D[16000:16800], I[16000:16800], Dr, Ir, 20, 6000, scale=np.sqrt(128.0))
