@@ -331,7 +331,8 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "strong", "vs_baseline": None, "dtype": "bf16 tensor-core first pass + f32 exact rescoring",
+            "scaling": "strong", "vs_baseline": None, "dtype": "bf16",
+            "dtype_detail": "bf16 tcgen05 first pass (fp32 accumulate) + f32 exact rescoring of the k' candidates",
             "data": "synthetic",
             "config": {"workload": HEADLINE["name"] if (nq, n, k) == (HEADLINE["nq"], HEADLINE["n"], HEADLINE["k"])
                        else f"custom: {nq} queries x {n}x{DIM}, k={k}",
@@ -342,7 +343,9 @@ def main():
             "roofline": roof,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12},
+                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12 * world,
+                    "note": "whole-job bytes: each query row crosses PCIe once (ranks upload 1/N slices and "
+                            "all-gather them over NVLink when N>1); every rank downloads the merged [nq,k] result"},
             "gpu_launches": launches,
             "clocks": clocks,
             "search_stats": stats,

@@ -154,6 +154,7 @@ struct drt_store {
     bool attrs_set = false;
     std::vector<cudaEvent_t> ev;   // per-launch timing events (DRT_SEARCH_TIME_KERNELS)
     int64_t exact_queries = 0;     // queries of the last search that needed the exact fp32 first pass
+    mutable std::mutex mu;         // add / search / reset / reconstruct on one store are serialised
 };
 
 namespace {
@@ -525,6 +526,7 @@ int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device
     if (!s) return fail(DRT_E_INVALID, "store is NULL");
     if (n < 0 || (n > 0 && !rows)) return fail(DRT_E_INVALID, "bad rows/n");
     if (n == 0) return DRT_OK;
+    std::lock_guard<std::mutex> lk(s->mu);
     if (s->ntotal + n > 0xFFFFFF00ll) return fail(DRT_E_UNSUPPORTED, "a shard holds at most 2^32-256 rows");
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -566,12 +568,14 @@ int drt_store_device(const drt_store* s) { return s ? s->device : -1; }
 
 int drt_store_reset(drt_store* s) {
     if (!s) return fail(DRT_E_INVALID, "store is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
     s->ntotal = 0;
     return DRT_OK;
 }
 
 int drt_store_reconstruct(const drt_store* s, int64_t row0, int64_t n, float* out, int out_on_device, void* stream) {
     if (!s || (n > 0 && !out)) return fail(DRT_E_INVALID, "bad arguments");
+    std::lock_guard<std::mutex> lk(s->mu);
     if (row0 < 0 || n < 0 || row0 + n > s->ntotal) return fail(DRT_E_INVALID, "rows [%lld,%lld) out of range", (long long)row0, (long long)(row0 + n));
     DeviceGuard g(s->device);
     cudaStream_t st = (cudaStream_t)stream;
@@ -595,6 +599,7 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
     if (k > DRT_MAX_K) return fail(DRT_E_UNSUPPORTED, "k=%d exceeds DRT_MAX_K=%d", k, DRT_MAX_K);
     if (nq == 0) return DRT_OK;
     if (!q || !out_scores || !out_ids) return fail(DRT_E_INVALID, "NULL query/output pointer");
+    std::lock_guard<std::mutex> lk(s->mu);
     int rc = check_device(s->device);
     if (rc != DRT_OK) return rc;
     DeviceGuard g(s->device);

@@ -55,6 +55,15 @@ def _cuda_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int, sorted_uniq
     return D, I
 
 
+def _to_host(dev, *tensors):
+    """Device tensors -> numpy arrays backed by (cached) pinned host blocks, one sync for all."""
+    outs = [torch.empty(t.shape, dtype=t.dtype, pin_memory=True) for t in tensors]
+    for o, t in zip(outs, tensors):
+        o.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(dev).synchronize()
+    return tuple(o.numpy() for o in outs)
+
+
 def shard_offsets(counts) -> list[int]:
     """Global id of each shard's first row, rank-major (exclusive prefix sum) + total."""
     off = [0]
@@ -132,11 +141,11 @@ class ShardedCorpusStore:
         host_in = isinstance(q, np.ndarray)
         dev = getattr(self.shards[0], "device", None)
         if host_in and dev is not None and torch.cuda.is_available():
-            # host queries: one H2D copy, the device path end to end, one D2H copy of the merged
-            # result (instead of bouncing every shard's candidates through host memory)
-            qd = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).cuda(dev, non_blocking=True)
+            # host queries: the device path end to end, one D2H copy of the merged result (instead
+            # of bouncing every shard's candidates through host memory)
+            qd = self._upload_queries(np.ascontiguousarray(q, dtype=np.float32), dev)
             Dm, Im = self.search(qd, k)
-            return Dm.cpu().numpy(), Im.cpu().numpy()
+            return _to_host(dev, Dm, Im)
         if self.distributed:
             D, I = self.shards[0].search(q, k, id_offset=self._offsets[self.rank])
             as_numpy = isinstance(D, np.ndarray)
@@ -158,6 +167,26 @@ class ShardedCorpusStore:
         if as_numpy:
             return Dm.cpu().numpy(), Im.cpu().numpy()
         return Dm, Im
+
+    # host query bytes above which a rank uploads only its 1/W slice over PCIe and the ranks
+    # all-gather the slices over NVLink (every rank passes the same queries to `search`)
+    SLICE_UPLOAD_MIN_BYTES = 1 << 20
+
+    def _upload_queries(self, qn: np.ndarray, dev) -> torch.Tensor:
+        Q, d = qn.shape
+        W = self.world
+        if not (self.distributed and W > 1 and Q >= W and qn.nbytes >= self.SLICE_UPLOAD_MIN_BYTES
+                and dist.get_backend(self.group) == "nccl"):
+            return torch.from_numpy(qn).cuda(dev, non_blocking=True)
+        per = -(-Q // W)
+        lo = min(self.rank * per, Q)
+        hi = min(lo + per, Q)
+        local = torch.zeros((per, d), dtype=torch.float32, device=torch.device("cuda", dev))
+        if hi > lo:
+            local[:hi - lo].copy_(torch.from_numpy(qn[lo:hi]), non_blocking=True)
+        full = torch.empty((W * per, d), dtype=torch.float32, device=local.device)
+        dist.all_gather_into_tensor(full, local, group=self.group)
+        return full[:Q]
 
     # candidate entries per rank above which the exchange switches from all-gather (every rank
     # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged

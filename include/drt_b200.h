@@ -40,7 +40,10 @@ extern "C" {
 #define DRT_SEARCH_FORCE_2CTA     4u  /* use the CTA-pair (M=256, cta_group::2) variant       */
 #define DRT_SEARCH_TIME_KERNELS    8u  /* bracket every MMA-filter launch with CUDA events     */
 
-typedef struct drt_store drt_store;   /* opaque: one device-resident corpus shard */
+/* opaque: one device-resident corpus shard.  A store owns its search workspace, so add / search /
+ * reset / reconstruct on ONE store are serialised by an internal lock (host threads may share a
+ * store; different stores run concurrently). */
+typedef struct drt_store drt_store;
 
 /* ---- library ------------------------------------------------------------------------------ */
 

@@ -396,3 +396,33 @@ def test_query_count_above_internal_batch():
     np.testing.assert_array_equal(D, Dd.cpu().numpy())
     Dr, Ir = flat_ip.flat_ip_search(x, q[16000:16800], 20)       # rows straddling the batch boundary
     _check_parity(D[16000:16800], I[16000:16800], Dr, Ir, 20, 6000, scale=np.sqrt(128.0))
+
+
+def test_host_threads_sharing_one_store():
+    """Two host threads searching the same store at once (ctypes drops the GIL): calls are
+    serialised inside the library, so both get the results a sequential run gives."""
+    import threading
+
+    rng = np.random.default_rng(91)
+    x = rng.standard_normal((30000, 256), dtype=np.float32)
+    qs = [rng.standard_normal((257, 256), dtype=np.float32) for _ in range(2)]
+    index = _mk(d=256, seg_rows=4096)
+    index.add(x)
+    want = [index.search(q, 50) for q in qs]
+    got = [None, None]
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(20):
+                got[i] = index.search(qs[i], 50)
+        except Exception as e:  # pragma: no cover
+            errs.append(e)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs
+    for (D, I), (Dw, Iw) in zip(got, want):
+        np.testing.assert_array_equal(I, Iw)
+        np.testing.assert_array_equal(D, Dw)

@@ -47,8 +47,15 @@ for k in (100, 1000):
     ok = ok and same
 Dn, In = store.search(q.cpu().numpy(), 100)               # host-buffer API
 Df, If = full.search(q, 100)
-res["numpy_api"] = bool(np.array_equal(In, If.cpu().numpy()))
+res["numpy_api"] = bool(np.array_equal(In, If.cpu().numpy()) and np.array_equal(Dn, Df.cpu().numpy()))
 ok = ok and res["numpy_api"]
+Dn, In = store.search(q.cpu().numpy()[:997], 100)         # ragged slice upload (997 % world != 0)
+res["numpy_api_ragged"] = bool(np.array_equal(In, If.cpu().numpy()[:997]) and np.array_equal(Dn, Df.cpu().numpy()[:997]))
+ok = ok and res["numpy_api_ragged"]
+store.SLICE_UPLOAD_MIN_BYTES = 1 << 62                    # whole-batch upload on every rank
+Dn, In = store.search(q.cpu().numpy(), 100)
+res["numpy_api_full_upload"] = bool(np.array_equal(In, If.cpu().numpy()))
+ok = ok and res["numpy_api_full_upload"]
 res["ok"] = ok
 print(json.dumps(res), flush=True)
 dist.barrier()
