@@ -169,6 +169,16 @@ int kprime_for(int k) {
     return (k + margin + 3) & ~3;
 }
 
+// CTA-pair tiles (M=256) halve the corpus-operand smem/L2 traffic per FLOP and run ~10 % faster
+// per padded query row than M=128 tiles (profiles/r1_q_sweep.md), but pad the query count to a
+// multiple of 256: pick the variant with the smaller padded cost.  With <= 128 queries half of
+// a pair tile would be padding and the pass is HBM-bound anyway.
+int default_ctas(int64_t nq) {
+    const int64_t pad1 = (nq + drt::kTileM - 1) / drt::kTileM * drt::kTileM;
+    const int64_t pad2 = (nq + 2 * drt::kTileM - 1) / (2 * drt::kTileM) * (2 * drt::kTileM);
+    return (10 * pad2 <= 11 * pad1) ? 2 : 1;
+}
+
 int set_kernel_attrs(drt_store* s) {
     if (s->attrs_set) return DRT_OK;
     CUDA_TRY(cudaFuncSetAttribute(drt::mips_filter_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -413,7 +423,7 @@ int refine_flagged(drt_store* s, const float* q_dev, int64_t nq, int k, float* o
         drt::gather_rows_kernel<<<(int)std::min<int64_t>(nf, 4096), 192, 0, st>>>(
             q_dev, (const int*)s->sub_idx.p, (float*)s->sub_q.p, s->dim, (int)nf);
         int64_t still = 0;
-        const int kctas = (flags & DRT_SEARCH_FORCE_1CTA) ? 1 : (flags & DRT_SEARCH_FORCE_2CTA) ? 2 : (nf > drt::kTileM ? 2 : 1);
+        const int kctas = (flags & DRT_SEARCH_FORCE_1CTA) ? 1 : (flags & DRT_SEARCH_FORCE_2CTA) ? 2 : default_ctas(nf);
         rc = search_retrying(s, (const float*)s->sub_q.p, nf, k, (float*)s->sub_os.p, (int64_t*)s->sub_oi.p, id_offset,
                              flags, st, kctas, keep, (unsigned char*)s->sub_flag.p, &still);
         if (rc != DRT_OK) return rc;
@@ -608,9 +618,7 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
     for (int i = 0; i < 12; ++i) s->stats[i] = 0;
     s->exact_queries = 0;
 
-    // CTA-pair tiles (M=256) halve the corpus-operand smem/L2 traffic per FLOP; with <= 128
-    // queries half of a pair tile would be padding and the pass is HBM-bound anyway.
-    int kctas = (nq > drt::kTileM) ? 2 : 1;
+    int kctas = default_ctas(nq);
     if (const char* e = getenv("DRT_B200_CTAS")) kctas = (atoi(e) == 2) ? 2 : 1;
     if (flags & DRT_SEARCH_FORCE_1CTA) kctas = 1;
     if (flags & DRT_SEARCH_FORCE_2CTA) kctas = 2;

@@ -31,7 +31,7 @@ for k in ks:
                 index.search(q, k, flags=flags)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            reps = 3
+            reps = int(os.environ.get("SWEEP_REPS", 3))
             e0.record()
             fns = 0
             for _ in range(reps):
@@ -42,5 +42,8 @@ for k in ks:
             ms = e0.elapsed_time(e1) / reps
             fms = fns / 1e6 / reps
             tf = 2.0 * nq * n * bench.DIM / (fms / 1e3) / 1e12
+            pk = bench.peaks()
+            roof_ms = max(n * bench.DIM * 2 / (pk["hbm"] * 1e9), 2.0 * nq * n * bench.DIM / (pk["bf16"] * 1e12)) * 1e3
             print(json.dumps(dict(k=k, nq=nq, ctas=ctas, ms=round(ms, 3), qps=round(nq / ms * 1e3, 1), filter_ms=round(fms, 3),
-                                  filter_tflops=round(tf, 1), stats=index.search_stats())), flush=True)
+                                  filter_tflops=round(tf, 1), roofline_ms=round(roof_ms, 3),
+                                  frac_of_roofline_step=round(roof_ms / ms, 3), frac_of_roofline_k1=round(roof_ms / fms, 3), stats=index.search_stats())), flush=True)
