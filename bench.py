@@ -243,8 +243,7 @@ def main():
 
     def step_device():
         if store is not None:
-            D, I = index.search(q_dev, k, id_offset=store._offsets[rank], flags=flags)
-            return store._exchange_and_merge(D, I, k)     # same exchange + merge store.search() runs
+            return store.search(q_dev, k, flags=flags)    # local shard search + exchange + merge
         return index.search(q_dev, k, flags=flags)
 
     def step_host():
@@ -337,6 +336,7 @@ def main():
             "config": {"workload": HEADLINE["name"] if (nq, n, k) == (HEADLINE["nq"], HEADLINE["n"], HEADLINE["k"])
                        else f"custom: {nq} queries x {n}x{DIM}, k={k}",
                        "nq": nq, "n": n, "dim": DIM, "k": k, "sharding": f"rows/{world}",
+                       "shard_depth": store.last_search.get("local_depth") if store is not None else k,
                        "l2": "inputs larger than L2 (13.5 GB bf16 corpus streamed per step); no flush",
                        "ctas_per_tile": stats["ctas_per_tile"], "kprime": stats["kprime"],
                        "corpus_chunks": stats["chunks"], "store_build_s": build_s},

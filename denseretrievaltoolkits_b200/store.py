@@ -16,6 +16,7 @@ shards on ONE GPU and runs the same search + merge path, so the merge is testabl
 """
 from __future__ import annotations
 
+import math
 from typing import Callable, Optional
 
 import numpy as np
@@ -23,6 +24,8 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+
+_NEG = -3.4028234663852886e38     # faiss' "no result" score
 
 
 def _cuda_merge(scores: torch.Tensor, ids: torch.Tensor, k_out: int, sorted_unique: bool = False):
@@ -91,6 +94,8 @@ class ShardedCorpusStore:
         self.shards = [index_factory() for _ in range(n_local)]
         self._offsets: Optional[list[int]] = None
         self._next_virtual = 0
+        self._reduce_depth = True
+        self.last_search = {}
 
     # ---- ingest -----------------------------------------------------------------------------
     def add(self, rows, shard: Optional[int] = None) -> None:
@@ -133,7 +138,31 @@ class ShardedCorpusStore:
         return self._offsets[-1]
 
     # ---- search -----------------------------------------------------------------------------
-    def search(self, q, k: int):
+    def local_depth(self, k: int) -> int:
+        """Depth every shard is searched to for a global top-k.
+
+        With rows dealt to W shards independently of the queries, a shard holds Binomial(k, 1/W)
+        of a query's global top-k, so mean + 6 sigma entries per shard suffice almost surely
+        (k=100, W=8: 40 instead of 100; k=1000, W=8: 192) — and rescoring, the candidate
+        exchange and the merge all shrink with it.  The result stays EXACT: after the merge a
+        query whose global k-th score does not lie strictly above the last entry of every
+        truncated shard list is searched again at full depth (`_truncated`), and a store whose
+        row order turns out to be correlated with the queries stops reducing the depth."""
+        W = self.world
+        if W <= 1 or not self._reduce_depth:
+            return k
+        p = 1.0 / W
+        kl = int(math.ceil((k * p + 6.0 * math.sqrt(k * p * (1.0 - p)) + 4.0) / 8.0) * 8)
+        return min(k, max(kl, -(-k // W)))
+
+    @staticmethod
+    def _truncated(S: torch.Tensor, Dm: torch.Tensor, k: int) -> torch.Tensor:
+        """S [W,Q,kl] shard lists, Dm [Q,k] merged: True where some shard's list is full and its
+        last score is not strictly below the global k-th (it may hold further top-k rows)."""
+        last = S[:, :, -1]
+        return ((last >= Dm[:, k - 1].unsqueeze(0)) & (last > _NEG)).any(0)
+
+    def search(self, q, k: int, flags: int = 0):
         """Every rank passes the SAME queries (CLI / benchmark use) and receives the global
         (D [Q,k], I [Q,k]).  Collective: all ranks must call with equal (Q, k)."""
         if self._offsets is None:
@@ -144,29 +173,104 @@ class ShardedCorpusStore:
             # host queries: the device path end to end, one D2H copy of the merged result (instead
             # of bouncing every shard's candidates through host memory)
             qd = self._upload_queries(np.ascontiguousarray(q, dtype=np.float32), dev)
-            Dm, Im = self.search(qd, k)
+            Dm, Im = self.search(qd, k, flags)
             return _to_host(dev, Dm, Im)
+        kl = self.local_depth(k)
+        Dm, Im, bad = self._search_merged(q, k, kl, flags)
+        self.last_search = {"local_depth": kl, "requeried": 0}
+        if bad is not None:
+            nbad = int(bad.sum().item())          # same value on every rank (computed from exchanged data)
+            if nbad:
+                idx = bad.nonzero().squeeze(1)
+                qt = torch.from_numpy(q) if host_in else q
+                qb = qt.index_select(0, idx.to(qt.device))
+                Db, Ib, _ = self._search_merged(qb.numpy() if host_in else qb, k, k, flags)
+                Dm[idx] = Db
+                Im[idx] = Ib
+                self.last_search["requeried"] = nbad
+                if 4 * nbad > Dm.shape[0]:
+                    self._reduce_depth = False     # row order correlates with the queries
+        if host_in:
+            return Dm.cpu().numpy(), Im.cpu().numpy()
+        return Dm, Im
+
+    def _search_merged(self, q, k: int, kl: int, flags: int):
+        """Depth-kl search of every shard, candidate exchange, merge to depth k.
+        Returns torch (D [Q,k], I [Q,k], truncated-mask [Q] or None when kl == k)."""
         if self.distributed:
-            D, I = self.shards[0].search(q, k, id_offset=self._offsets[self.rank])
-            as_numpy = isinstance(D, np.ndarray)
-            if as_numpy:
+            D, I = self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags)
+            if isinstance(D, np.ndarray):
                 D, I = torch.from_numpy(D), torch.from_numpy(I)
                 if dist.get_backend(self.group) == "nccl":
                     D, I = D.cuda(self.shards[0].device), I.cuda(self.shards[0].device)
-            Dm, Im = self._exchange_and_merge(D, I, k)
-            if as_numpy:
-                return Dm.cpu().numpy(), Im.cpu().numpy()
-            return Dm, Im
-        parts = [s.search(q, k, id_offset=self._offsets[g]) for g, s in enumerate(self.shards)]
-        as_numpy = isinstance(parts[0][0], np.ndarray)
-        if as_numpy:
+            return self._exchange_and_merge(D, I, k, check=kl < k)
+        parts = [s.search(q, kl, id_offset=self._offsets[g], flags=flags) for g, s in enumerate(self.shards)]
+        if isinstance(parts[0][0], np.ndarray):
             dev = getattr(self.shards[0], "device", None)
             to_t = (lambda a: torch.from_numpy(a).cuda(dev)) if dev is not None and torch.cuda.is_available() else torch.from_numpy
             parts = [(to_t(d), to_t(i)) for d, i in parts]
-        Dm, Im = self._merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]), k)
-        if as_numpy:
-            return Dm.cpu().numpy(), Im.cpu().numpy()
-        return Dm, Im
+        S = torch.stack([p[0] for p in parts])
+        Dm, Im = self._merge(S, torch.stack([p[1] for p in parts]), k)
+        return Dm, Im, (self._truncated(S, Dm, k) if kl < k else None)
+
+    # candidate entries per rank above which the exchange switches from all-gather (every rank
+    # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged
+    # [Q/W, k] slices are all-gathered): W x fewer bytes received and W x less merge work
+    A2A_MIN_ENTRIES = 1 << 20
+    A2A_MIN_WORLD = 4
+
+    def _exchange_and_merge(self, D: torch.Tensor, I: torch.Tensor, k: int, check: bool = False):
+        """D, I: this rank's [Q, kl] lists.  Returns (Dm [Q,k], Im [Q,k], truncated-mask | None)."""
+        W = self.world
+        Q, kl = D.shape
+        if W >= self.A2A_MIN_WORLD and Q * kl >= self.A2A_MIN_ENTRIES and Q >= W:
+            per = -(-Q // W)
+            if per * W != Q:     # pad the query axis so it splits evenly; padding rows are dropped below
+                padD = torch.full((per * W - Q, kl), _NEG, dtype=D.dtype, device=D.device)
+                padI = torch.full((per * W - Q, kl), -1, dtype=I.dtype, device=I.device)
+                D, I = torch.cat([D, padD]), torch.cat([I, padI])
+            rD, rI = torch.empty_like(D), torch.empty_like(I)
+            dist.all_to_all_single(rD, D.contiguous(), group=self.group)    # rD[g] = rank g's list for MY query slice
+            dist.all_to_all_single(rI, I.contiguous(), group=self.group)
+            mD, mI = self._merge(rD.view(W, per, kl), rI.view(W, per, kl), k)
+            oD = torch.empty((W * per, k), dtype=D.dtype, device=D.device)
+            oI = torch.empty((W * per, k), dtype=I.dtype, device=I.device)
+            dist.all_gather_into_tensor(oD, mD.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(oI, mI.contiguous(), group=self.group)
+            bad = None
+            if check:
+                mine = self._truncated(rD.view(W, per, kl), mD, k).to(torch.uint8)
+                allbad = torch.empty((W * per,), dtype=torch.uint8, device=D.device)
+                dist.all_gather_into_tensor(allbad, mine, group=self.group)
+                bad = allbad[:Q].bool()
+            return oD[:Q], oI[:Q], bad
+        if D.is_cuda:
+            # gather straight into the [W, Q, kl] layout the merge kernel reads (no list copies)
+            gD = torch.empty((W * Q, kl), dtype=D.dtype, device=D.device)
+            gI = torch.empty((W * Q, kl), dtype=I.dtype, device=I.device)
+            dist.all_gather_into_tensor(gD, D.contiguous(), group=self.group)
+            dist.all_gather_into_tensor(gI, I.contiguous(), group=self.group)
+            S, Si = gD.view(W, Q, kl), gI.view(W, Q, kl)
+        else:
+            Ds = [torch.empty_like(D) for _ in range(W)]
+            Is = [torch.empty_like(I) for _ in range(W)]
+            dist.all_gather(Ds, D, group=self.group)
+            dist.all_gather(Is, I, group=self.group)
+            S, Si = torch.stack(Ds), torch.stack(Is)
+        Dm, Im = self._merge(S, Si, k)
+        return Dm, Im, (self._truncated(S, Dm, k) if check else None)
+
+    def search_local_queries(self, q_local, k: int):
+        """Trainer.evaluate use (trainer.py:287-297): every rank holds its OWN query batch
+        (equal sizes).  Queries are all-gathered, searched against every shard, and each rank
+        gets back the global top-k of its own queries."""
+        if not self.distributed:
+            return self.search(q_local, k)
+        qs = [torch.empty_like(q_local) for _ in range(self.world)]
+        dist.all_gather(qs, q_local.contiguous(), group=self.group)
+        D, I = self.search(torch.cat(qs, dim=0), k)
+        n = q_local.shape[0]
+        return D[self.rank * n:(self.rank + 1) * n], I[self.rank * n:(self.rank + 1) * n]
 
     # host query bytes above which a rank uploads only its 1/W slice over PCIe and the ranks
     # all-gather the slices over NVLink (every rank passes the same queries to `search`)
@@ -187,51 +291,3 @@ class ShardedCorpusStore:
         full = torch.empty((W * per, d), dtype=torch.float32, device=local.device)
         dist.all_gather_into_tensor(full, local, group=self.group)
         return full[:Q]
-
-    # candidate entries per rank above which the exchange switches from all-gather (every rank
-    # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged
-    # [Q/W, k] slices are all-gathered): W x fewer bytes received and W x less merge work
-    A2A_MIN_ENTRIES = 1 << 20
-    A2A_MIN_WORLD = 4
-
-    def _exchange_and_merge(self, D: torch.Tensor, I: torch.Tensor, k: int):
-        W = self.world
-        Q = D.shape[0]
-        if W >= self.A2A_MIN_WORLD and Q * k >= self.A2A_MIN_ENTRIES and Q >= W:
-            per = -(-Q // W)
-            if per * W != Q:     # pad the query axis so it splits evenly; padding rows are dropped below
-                padD = torch.full((per * W - Q, k), -3.4028234663852886e38, dtype=D.dtype, device=D.device)
-                padI = torch.full((per * W - Q, k), -1, dtype=I.dtype, device=I.device)
-                D, I = torch.cat([D, padD]), torch.cat([I, padI])
-            rD, rI = torch.empty_like(D), torch.empty_like(I)
-            dist.all_to_all_single(rD, D.contiguous(), group=self.group)    # rD[g] = rank g's list for MY query slice
-            dist.all_to_all_single(rI, I.contiguous(), group=self.group)
-            mD, mI = self._merge(rD.view(W, per, k), rI.view(W, per, k), k)
-            oD, oI = torch.empty_like(D), torch.empty_like(I)
-            dist.all_gather_into_tensor(oD, mD.contiguous(), group=self.group)
-            dist.all_gather_into_tensor(oI, mI.contiguous(), group=self.group)
-            return oD[:Q], oI[:Q]
-        if D.is_cuda:
-            # gather straight into the [W, Q, k] layout the merge kernel reads (no list copies)
-            gD = torch.empty((W * Q, k), dtype=D.dtype, device=D.device)
-            gI = torch.empty((W * Q, k), dtype=I.dtype, device=I.device)
-            dist.all_gather_into_tensor(gD, D.contiguous(), group=self.group)
-            dist.all_gather_into_tensor(gI, I.contiguous(), group=self.group)
-            return self._merge(gD.view(W, Q, k), gI.view(W, Q, k), k)
-        Ds = [torch.empty_like(D) for _ in range(W)]
-        Is = [torch.empty_like(I) for _ in range(W)]
-        dist.all_gather(Ds, D, group=self.group)
-        dist.all_gather(Is, I, group=self.group)
-        return self._merge(torch.stack(Ds), torch.stack(Is), k)
-
-    def search_local_queries(self, q_local, k: int):
-        """Trainer.evaluate use (trainer.py:287-297): every rank holds its OWN query batch
-        (equal sizes).  Queries are all-gathered, searched against every shard, and each rank
-        gets back the global top-k of its own queries."""
-        if not self.distributed:
-            return self.search(q_local, k)
-        qs = [torch.empty_like(q_local) for _ in range(self.world)]
-        dist.all_gather(qs, q_local.contiguous(), group=self.group)
-        D, I = self.search(torch.cat(qs, dim=0), k)
-        n = q_local.shape[0]
-        return D[self.rank * n:(self.rank + 1) * n], I[self.rank * n:(self.rank + 1) * n]

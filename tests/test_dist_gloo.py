@@ -58,6 +58,15 @@ def _worker(rank, world, port, out_dir):
     offs = st.finalize()
     assert offs == split, offs
     D, I = st.search(q, 20)
+    D2, I2 = st.search(q, 200)                     # reduced per-shard depth (152 of 200)
+    depth2 = dict(st.last_search)
+    # rows correlated with the queries: shard 0 owns the whole top-200 -> truncation check -> re-query
+    xc = x.copy()
+    xc[:430] *= 5.0
+    stc = ShardedCorpusStore(32, index_factory=lambda: _OracleIndex(32), merge_fn=_oracle_merge)
+    stc.add(xc[split[rank]:split[rank + 1]])
+    Dc, Ic = stc.search(q, 200)
+    depthc = dict(stc.last_search)
     Dl, Il = st.search_local_queries(torch.from_numpy(q[rank * 3:(rank + 1) * 3]), 20)
     t = torch.full((2, 3), float(rank), requires_grad=True)
     g = gather_rank_major(t, rank, world)
@@ -65,7 +74,8 @@ def _worker(rank, world, port, out_dir):
     from denseretrievaltoolkits_b200.evaluation import reduce_metrics
 
     red = reduce_metrics({"Recall@5": 2.0 + rank, "MRR@5": 1.0, "query_num": 0}, 3 + rank)   # per-rank sums
-    np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, Dl=np.asarray(Dl), Il=np.asarray(Il),
+    np.savez(os.path.join(out_dir, f"r{rank}.npz"), D=D, I=I, I2=I2, Ic=Ic,
+             depth=np.array([depth2["local_depth"], depth2["requeried"], depthc["local_depth"], depthc["requeried"]]), Dl=np.asarray(Dl), Il=np.asarray(Il),
              g=g.detach().numpy(), grad=t.grad.numpy(), red=np.array([red["Recall@5"], red["MRR@5"], red["query_num"]]))
     dist.destroy_process_group()
 
@@ -83,6 +93,11 @@ def test_sharded_store_two_ranks_gloo(tmp_path):
         np.testing.assert_array_equal(r["I"], Ir)          # G-shard result == 1-shard result, ids bit-for-bit
         np.testing.assert_allclose(r["D"], Dr, rtol=1e-6)
         np.testing.assert_array_equal(r["Il"], Ir[rank * 3:(rank + 1) * 3])
+        np.testing.assert_array_equal(r["I2"], flat_ip.flat_ip_search(x, q, 200)[1])
+        xc = x.copy()
+        xc[:430] *= 5.0
+        np.testing.assert_array_equal(r["Ic"], flat_ip.flat_ip_search(xc, q, 200)[1])
+        assert r["depth"][0] == 152 and r["depth"][2] == 152 and r["depth"][3] == 6, r["depth"]
         # rank-major gather; gradient flows only into the local slot (biencoder.py:251)
         np.testing.assert_array_equal(r["g"], np.repeat([[0.0], [1.0]], 2, axis=0).repeat(3, axis=1).reshape(4, 3))
         np.testing.assert_array_equal(r["grad"], np.ones((2, 3)))

@@ -239,6 +239,44 @@ def test_virtual_shards_equal_single_store():
         D, I = st.search(q, 100)
         np.testing.assert_array_equal(I, Is)
         np.testing.assert_array_equal(D, Ds)
+        assert st.last_search["local_depth"] == {2: 88, 4: 56, 8: 40}[G]      # reduced per-shard depth
+
+
+def test_reduced_shard_depth_requeries_when_rows_correlate_with_queries():
+    """Shards are searched to mean + 6 sigma of their expected share of the top-k; when one shard
+    holds (nearly) the whole top-k the truncation check fires, those queries are searched again
+    at full depth, the result is still bit-identical to one store, and the store stops reducing."""
+    from denseretrievaltoolkits_b200.store import ShardedCorpusStore
+
+    rng = np.random.default_rng(12)
+    x = rng.standard_normal((40000, 256), dtype=np.float32)
+    x[:5000] *= 3.0                                  # shard 0 of 8 owns every query's top-k
+    q = rng.standard_normal((64, 256), dtype=np.float32)
+    single = _mk(d=256, seg_rows=4096)
+    single.add(x)
+    Ds, Is = single.search(q, 100)
+    st = ShardedCorpusStore(256, num_virtual_shards=8, device=0, seg_rows=4096)
+    st.add_split(x)
+    D, I = st.search(q, 100)
+    np.testing.assert_array_equal(I, Is)
+    np.testing.assert_array_equal(D, Ds)
+    assert st.last_search == {"local_depth": 40, "requeried": 64}
+    D, I = st.search(torch.from_numpy(q).cuda(), 100)          # now at full depth, device tensors
+    assert st.last_search == {"local_depth": 100, "requeried": 0}
+    np.testing.assert_array_equal(I.cpu().numpy(), Is)
+    # a few queries only: mixed result rows
+    x2 = rng.standard_normal((40000, 256), dtype=np.float32)
+    q2 = rng.standard_normal((64, 256), dtype=np.float32)
+    x2[:60] = 6.0 * q2[5] / np.linalg.norm(q2[5]) + 0.01 * x2[:60]    # 60 of query 5's top-100 sit in shard 0
+    single2 = _mk(d=256, seg_rows=4096)
+    single2.add(x2)
+    Ds2, Is2 = single2.search(q2, 100)
+    st2 = ShardedCorpusStore(256, num_virtual_shards=8, device=0, seg_rows=4096)
+    st2.add_split(x2)
+    D2, I2 = st2.search(q2, 100)
+    np.testing.assert_array_equal(I2, Is2)
+    np.testing.assert_array_equal(D2, Ds2)
+    assert 1 <= st2.last_search["requeried"] <= 8 and st2._reduce_depth
 
 
 @pytest.mark.parametrize("k", [100, 1000])
