@@ -137,7 +137,8 @@ inline bool aligned16_ptr(const void* p) { return (reinterpret_cast<uintptr_t>(p
 
 // =============================================================================================
 struct drt_store {
-    int dim = 0;
+    int dim = 0;          // row pitch in elements: the caller's dim rounded up to a multiple of 64, zero padded
+    int dim_user = 0;     // the caller's embedding dim (rows / queries / reconstruct use this pitch)
     int device = 0;
     int64_t seg_rows = 0;
     int64_t ntotal = 0;
@@ -493,7 +494,10 @@ int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows) {
     if (!out) return fail(DRT_E_INVALID, "out is NULL");
     *out = nullptr;
     if (dim <= 0) return fail(DRT_E_INVALID, "dim must be positive, got %d", dim);
-    if (dim % 64 != 0) return fail(DRT_E_UNSUPPORTED, "dim %d is not a multiple of 64 (one 128-byte bf16 swizzle span)", dim);
+    if (dim > 8192) return fail(DRT_E_UNSUPPORTED, "dim %d exceeds 8192", dim);
+    // one TMA box spans 64 bf16 (a 128-byte swizzle row): other dims are stored zero-padded to
+    // the next multiple of 64, which changes no inner product
+    const int dim_pad = (dim + 63) / 64 * 64;
     if (seg_rows == 0) seg_rows = 1 << 20;
     if (seg_rows < 256 || seg_rows % 256 != 0) return fail(DRT_E_INVALID, "seg_rows must be a positive multiple of 256");
     int rc = check_device(device);
@@ -502,7 +506,7 @@ int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows) {
     if (!g.ok) return fail(DRT_E_CUDA, "cudaSetDevice(%d) failed", device);
     drt_store* s = new (std::nothrow) drt_store();
     if (!s) return fail(DRT_E_OOM, "host allocation failed");
-    s->dim = dim; s->device = device; s->seg_rows = seg_rows;
+    s->dim = dim_pad; s->dim_user = dim; s->device = device; s->seg_rows = seg_rows;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaHostAlloc((void**)&s->err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&s->err_dev, s->err_host, 0) != cudaSuccess ||
@@ -554,12 +558,20 @@ int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device
                 return fail(DRT_E_OOM, "allocating corpus segment %lld (%lld rows x %d) failed: %s", (long long)seg,
                             (long long)s->seg_rows, s->dim, cudaGetErrorString(e));
             }
+            if (s->dim_user != s->dim) {   // padding columns stay zero for the life of the segment
+                e = cudaMemsetAsync(f, 0, (size_t)s->seg_rows * row_f32, st);
+                if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(f); cudaFree(b); return fail(DRT_E_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e)); }
+            }
             s->seg_f32.push_back(f); s->seg_bf16.push_back(b);
         }
         const int64_t take = std::min(n - done, s->seg_rows - off);
         float* dst = s->seg_f32[seg] + (size_t)off * s->dim;
-        CUDA_TRY(cudaMemcpyAsync(dst, rows + (size_t)done * s->dim, (size_t)take * row_f32,
-                                 rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+        const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+        if (s->dim_user == s->dim)
+            CUDA_TRY(cudaMemcpyAsync(dst, rows + (size_t)done * s->dim, (size_t)take * row_f32, kind, st));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(dst, row_f32, rows + (size_t)done * s->dim_user, (size_t)s->dim_user * 4,
+                                       (size_t)s->dim_user * 4, (size_t)take, kind, st));
         const size_t n4 = (size_t)take * s->dim / 4;
         const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)s->sm_count * 16);
         drt::f32_to_bf16_kernel<<<blocks, 256, 0, st>>>((const float4*)dst,
@@ -573,7 +585,7 @@ int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device
 }
 
 int64_t drt_store_ntotal(const drt_store* s) { return s ? s->ntotal : -1; }
-int drt_store_dim(const drt_store* s) { return s ? s->dim : -1; }
+int drt_store_dim(const drt_store* s) { return s ? s->dim_user : -1; }
 int drt_store_device(const drt_store* s) { return s ? s->device : -1; }
 
 int drt_store_reset(drt_store* s) {
@@ -593,9 +605,9 @@ int drt_store_reconstruct(const drt_store* s, int64_t row0, int64_t n, float* ou
     while (done < n) {
         const int64_t r = row0 + done, seg = r / s->seg_rows, off = r % s->seg_rows;
         const int64_t take = std::min(n - done, s->seg_rows - off);
-        CUDA_TRY(cudaMemcpyAsync(out + (size_t)done * s->dim, s->seg_f32[seg] + (size_t)off * s->dim,
-                                 (size_t)take * s->dim * 4,
-                                 out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpy2DAsync(out + (size_t)done * s->dim_user, (size_t)s->dim_user * 4,
+                                   s->seg_f32[seg] + (size_t)off * s->dim, (size_t)s->dim * 4, (size_t)s->dim_user * 4,
+                                   (size_t)take, out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
         done += take;
     }
     if (!out_on_device) CUDA_TRY(cudaStreamSynchronize(st));
@@ -630,16 +642,28 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
         const float* q_dev;
         float* os_dev;
         int64_t* oi_dev;
-        if (io_on_device) {
+        const bool padded = s->dim_user != s->dim;
+        if (io_on_device && !padded) {
             q_dev = q + (size_t)q0 * s->dim;
+        } else {
+            // host queries, or a dim that is stored zero-padded: stage into the padded workspace
+            if ((rc = s->q_f32.ensure((size_t)nb * s->dim * 4)) != DRT_OK) return rc;
+            const cudaMemcpyKind kind = io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+            if (padded) {
+                CUDA_TRY(cudaMemsetAsync(s->q_f32.p, 0, (size_t)nb * s->dim * 4, st));
+                CUDA_TRY(cudaMemcpy2DAsync(s->q_f32.p, (size_t)s->dim * 4, q + (size_t)q0 * s->dim_user, (size_t)s->dim_user * 4,
+                                           (size_t)s->dim_user * 4, (size_t)nb, kind, st));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(s->q_f32.p, q + (size_t)q0 * s->dim, (size_t)nb * s->dim * 4, kind, st));
+            }
+            q_dev = (const float*)s->q_f32.p;
+        }
+        if (io_on_device) {
             os_dev = out_scores + (size_t)q0 * k;
             oi_dev = out_ids + (size_t)q0 * k;
         } else {
-            if ((rc = s->q_f32.ensure((size_t)nb * s->dim * 4)) != DRT_OK) return rc;
             if ((rc = s->out_scores.ensure((size_t)nb * k * 4)) != DRT_OK) return rc;
             if ((rc = s->out_ids.ensure((size_t)nb * k * 8)) != DRT_OK) return rc;
-            CUDA_TRY(cudaMemcpyAsync(s->q_f32.p, q + (size_t)q0 * s->dim, (size_t)nb * s->dim * 4, cudaMemcpyHostToDevice, st));
-            q_dev = (const float*)s->q_f32.p;
             os_dev = (float*)s->out_scores.p;
             oi_dev = (int64_t*)s->out_ids.p;
         }

@@ -28,7 +28,7 @@ extern "C" {
 #define DRT_E_CUDA           -2   /* a CUDA runtime / driver call failed                   */
 #define DRT_E_NO_DEVICE      -3   /* no CUDA device, or the device is not sm_100 (B200)     */
 #define DRT_E_OOM            -4   /* device allocation failed                              */
-#define DRT_E_UNSUPPORTED    -5   /* e.g. dim % 64 != 0, k > DRT_MAX_K, non-"Flat" factory  */
+#define DRT_E_UNSUPPORTED    -5   /* e.g. dim > 8192, k > DRT_MAX_K, non-"Flat" factory      */
 #define DRT_E_INTERNAL       -6   /* kernel-side watchdog / invariant violation             */
 
 #define DRT_MAX_K          2048   /* same ceiling faiss-gpu uses for k-selection            */
@@ -58,7 +58,10 @@ int         drt_device_count(void);
  * _index_corpus / _load_index (DRT/trainer/trainer.py:191-262).                               */
 
 /* faiss.IndexFlatIP(d) (index.py:19,23).  `seg_rows` = rows per device segment (0 = default
- * 1<<20); rows live in fixed-size segments so `add` never reallocates or moves data. */
+ * 1<<20); rows live in fixed-size segments so `add` never reallocates or moves data.
+ * Any 1 <= dim <= 8192 (the reference's `projection_out_dim`, arguments.py:46, is free): rows
+ * are stored zero-padded to the next multiple of 64 elements, which changes no inner product;
+ * every pointer the caller passes or receives uses its own `dim` as the row pitch. */
 int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows);
 int drt_store_destroy(drt_store* s);
 

@@ -53,7 +53,7 @@ def test_no_cpu_fallback(built_lib):
 
 def test_argument_validation_without_device(built_lib):
     h = ctypes.c_void_p()
-    assert built_lib.drt_store_create(ctypes.byref(h), 100, 0, 0) == -5      # dim % 64
+    assert built_lib.drt_store_create(ctypes.byref(h), 100000, 0, 0) == -5   # dim > 8192
     assert built_lib.drt_store_create(ctypes.byref(h), -1, 0, 0) == -1
     assert built_lib.drt_store_create(ctypes.byref(h), 768, 0, 100) == -1    # seg_rows % 256
     assert built_lib.drt_merge_topk(0, None, None, 1, 1, 1, None, None, 0, 0, None) == -1

@@ -319,7 +319,7 @@ def test_scale_properties_2m_rows(k):
 
 @pytest.mark.parametrize("d", [64, 128, 384, 1024])
 def test_other_embedding_dims(d):
-    """dim is any multiple of 64 (one 128-byte bf16 swizzle span): MiniLM 384, BERT-large 1024..."""
+    """Multiples of 64 (one 128-byte bf16 swizzle span) are stored as they are: MiniLM 384, BERT-large 1024..."""
     rng = np.random.default_rng(d)
     x = rng.standard_normal((30000, d), dtype=np.float32)
     q = rng.standard_normal((150, d), dtype=np.float32)
@@ -328,10 +328,34 @@ def test_other_embedding_dims(d):
     D, I = index.search(q, 50)
     Dr, Ir = flat_ip.flat_ip_search(x, q, 50)
     _check_parity(D, I, Dr, Ir, 50, 30000, scale=np.sqrt(float(d)))
+
+
+@pytest.mark.parametrize("d", [1, 50, 100, 300, 770])
+def test_dims_that_are_not_multiples_of_64(d, tmp_path):
+    """`projection_out_dim` (arguments.py:46) is free in the reference: such rows are stored
+    zero-padded to the next multiple of 64, invisible through add / search / reconstruct / files."""
     from denseretrievaltoolkits_b200 import faiss_compat
 
-    with pytest.raises(RuntimeError):
-        faiss_compat.IndexFlatIP(100)          # not a multiple of 64: refused, no fallback
+    rng = np.random.default_rng(1000 + d)
+    x = rng.standard_normal((9000, d), dtype=np.float32)
+    q = rng.standard_normal((70, d), dtype=np.float32)
+    index = _mk(d=d, seg_rows=4096)
+    index.add(x[:5000])
+    index.add(torch.from_numpy(x[5000:]).cuda())            # device rows, unpadded pitch
+    assert index.d == d and index.ntotal == 9000
+    D, I = index.search(q, 30)
+    Dr, Ir = flat_ip.flat_ip_search(x, q, 30)
+    _check_parity(D, I, Dr, Ir, 30, 9000, scale=np.sqrt(float(d)))
+    Dd, Id = index.search(torch.from_numpy(q).cuda(), 30)   # device queries, unpadded pitch
+    np.testing.assert_array_equal(Id.cpu().numpy(), I)
+    np.testing.assert_array_equal(index.reconstruct_n(4090, 20), x[4090:4110])   # across a segment boundary
+    path = str(tmp_path / "idx.faiss")
+    faiss_compat.write_index(index, path)
+    again = faiss_compat.read_index(path)
+    assert again.d == d
+    D2, I2 = again.search(q, 30)
+    np.testing.assert_array_equal(I2, I)
+    np.testing.assert_array_equal(D2, D)
 
 
 def test_near_duplicate_corpus_falls_back_to_exact_fp32_pass():
