@@ -317,17 +317,18 @@ def test_scale_properties_2m_rows(k):
     assert torch.equal(I, I2) and torch.equal(D, D2)
 
 
-@pytest.mark.parametrize("d", [64, 128, 384, 1024])
+@pytest.mark.parametrize("d", [64, 128, 384, 1024, 4096, 8192])
 def test_other_embedding_dims(d):
     """Multiples of 64 (one 128-byte bf16 swizzle span) are stored as they are: MiniLM 384, BERT-large 1024..."""
     rng = np.random.default_rng(d)
-    x = rng.standard_normal((30000, d), dtype=np.float32)
+    n = 30000 if d <= 1024 else 6000
+    x = rng.standard_normal((n, d), dtype=np.float32)
     q = rng.standard_normal((150, d), dtype=np.float32)
-    index = _mk(d=d, seg_rows=8192)
+    index = _mk(d=d, seg_rows=8192 if d <= 1024 else 2048)
     index.add(x)
     D, I = index.search(q, 50)
     Dr, Ir = flat_ip.flat_ip_search(x, q, 50)
-    _check_parity(D, I, Dr, Ir, 50, 30000, scale=np.sqrt(float(d)))
+    _check_parity(D, I, Dr, Ir, 50, n, scale=np.sqrt(float(d)))
 
 
 @pytest.mark.parametrize("d", [1, 50, 100, 300, 770])
@@ -488,3 +489,21 @@ def test_host_threads_sharing_one_store():
     for (D, I), (Dw, Iw) in zip(got, want):
         np.testing.assert_array_equal(I, Iw)
         np.testing.assert_array_equal(D, Dw)
+
+
+def test_single_query_single_row_and_k1():
+    """Degenerate shapes: one query, one row, k = 1 (the sampler's retriever.search(query, n) shape)."""
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((1, 768), dtype=np.float32)
+    q = rng.standard_normal((1, 768), dtype=np.float32)
+    index = _mk(seg_rows=256)
+    index.add(x)
+    D, I = index.search(q, 1)
+    assert I.tolist() == [[0]] and abs(D[0, 0] - float(q[0] @ x[0])) <= 1e-4 * abs(D[0, 0]) + 1e-4
+    D, I = index.search(q, 3)
+    assert I.tolist() == [[0, -1, -1]]
+    x2 = rng.standard_normal((1000, 768), dtype=np.float32)
+    index.add(x2)
+    D, I = index.search(q, 1)
+    Dr, Ir = flat_ip.flat_ip_search(np.concatenate([x, x2]), q, 1)
+    np.testing.assert_array_equal(I, Ir)
