@@ -5,7 +5,7 @@ Reference call sites this module serves, unmodified:
   faiss.IndexFlatIP(d)                 DRT/evaluator/index.py:19,23
   index.add(x)                         index.py:28, DRT/trainer/trainer.py:235
   index.search(x, k) -> (D, I)         index.py:32
-  faiss.index_factory(d, str)          index.py:50   (only exact "Flat" + inner product)
+  faiss.index_factory(d, str)          index.py:50   (only exact "Flat"; faiss' default metric L2 -> IndexFlatL2)
   index.is_trained / train / verbose   index.py:52-54
   faiss.write_index / read_index       trainer.py:245,257
 
@@ -161,45 +161,152 @@ def _default_device() -> int:
     return 0
 
 
-def index_factory(d: int, description: str, metric: int = METRIC_INNER_PRODUCT):
-    """faiss.index_factory (index.py:50).  Only the exact configuration is served: "Flat" with
-    the inner-product metric; anything else (IVF/PQ/HNSW..., L2) is approximate or a different
-    metric and is refused rather than silently approximated."""
+_FLT_MAX = np.float32(3.4028234663852886e38)
+_L2_CHUNK = 1 << 18
+
+
+def _bf16_round(a: np.ndarray) -> np.ndarray:
+    """fp32 -> nearest-even bf16 -> fp32 (finite inputs)."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000).astype(np.uint32)
+    return u.view(np.float32)
+
+
+class IndexFlatL2:
+    """Exact squared-L2 index — what `faiss.index_factory(d, "Flat")` returns with faiss' default
+    metric, i.e. what the reference's `FaissRetriever(init_reps, "Flat")` (index.py:47-54) holds.
+
+    Runs on the inner-product store: argmin |q - x|^2 = argmax (q.x - |x|^2 / 2), so every row is
+    stored as [x, n1, n2, n3] with n1 + n2 + n3 = -|x|^2 / 2 split exactly into three
+    bf16-representable pieces (the tensor-core first pass sees the norm term to fp32 accuracy),
+    queries are searched as [q, 1, 1, 1], and D = |q|^2 - 2 * score, ascending."""
+
+    metric_type = METRIC_L2
+
+    def __init__(self, d: int, device: int | None = None, seg_rows: int = 0):
+        self.d = int(d)
+        self.is_trained = True
+        self.verbose = False
+        self._ip = IndexFlatIP(self.d + 3, device=device, seg_rows=seg_rows)
+
+    @property
+    def ntotal(self) -> int:
+        return self._ip.ntotal
+
+    @property
+    def device(self) -> int:
+        return self._ip.device
+
+    def train(self, x) -> None:
+        return None
+
+    def reset(self) -> None:
+        self._ip.reset()
+
+    def add(self, x) -> None:
+        if _is_torch_tensor(x) and x.is_cuda:
+            import torch
+
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise RuntimeError(f"add: expected [n,{self.d}], got {tuple(x.shape)}")
+            for r0 in range(0, x.shape[0], _L2_CHUNK):
+                xb = x[r0:r0 + _L2_CHUNK].detach().to(torch.float32)
+                nrm = -0.5 * (xb.double() * xb.double()).sum(1)
+                n1 = nrm.float().bfloat16().float()
+                n2 = (nrm - n1.double()).float().bfloat16().float()
+                n3 = (nrm - n1.double() - n2.double()).float().bfloat16().float()
+                self._ip.add(torch.cat([xb, n1[:, None], n2[:, None], n3[:, None]], dim=1))
+            return
+        if _is_torch_tensor(x):
+            x = x.detach().cpu().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise RuntimeError(f"add: expected [n,{self.d}] float32, got {x.shape}")
+        for r0 in range(0, x.shape[0], _L2_CHUNK):
+            xb = x[r0:r0 + _L2_CHUNK]
+            nrm = -0.5 * np.einsum("ij,ij->i", xb, xb, dtype=np.float64)
+            n1 = _bf16_round(nrm.astype(np.float32))
+            n2 = _bf16_round((nrm - n1).astype(np.float32))
+            n3 = _bf16_round((nrm - n1 - n2).astype(np.float32))
+            self._ip.add(np.concatenate([xb, n1[:, None], n2[:, None], n3[:, None]], axis=1))
+
+    def search(self, x, k: int, *, id_offset: int = 0, flags: int = 0):
+        if _is_torch_tensor(x) and x.is_cuda:
+            import torch
+
+            if x.dim() != 2 or x.shape[1] != self.d:
+                raise RuntimeError(f"search: expected [nq,{self.d}], got {tuple(x.shape)}")
+            xq = x.detach().to(torch.float32)
+            S, I = self._ip.search(torch.cat([xq, torch.ones((xq.shape[0], 3), dtype=torch.float32, device=xq.device)], dim=1),
+                                   k, id_offset=id_offset, flags=flags)
+            qn = (xq.double() * xq.double()).sum(1, keepdim=True)
+            D = torch.where(I < 0, torch.full_like(S, float(_FLT_MAX), dtype=torch.float64),
+                            (qn - 2.0 * S.double()).clamp_min_(0.0)).float()
+            return D, I
+        if _is_torch_tensor(x):
+            x = x.detach().numpy()
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise RuntimeError(f"search: expected [nq,{self.d}] float32, got {x.shape}")
+        S, I = self._ip.search(np.concatenate([x, np.ones((x.shape[0], 3), np.float32)], axis=1), k,
+                               id_offset=id_offset, flags=flags)
+        qn = np.einsum("ij,ij->i", x, x, dtype=np.float64)[:, None]
+        D = np.where(I < 0, np.float64(_FLT_MAX), np.maximum(qn - 2.0 * S.astype(np.float64), 0.0)).astype(np.float32)
+        return D, I
+
+    def search_stats(self) -> dict:
+        return self._ip.search_stats()
+
+    def reconstruct_n(self, i0: int = 0, n: int | None = None) -> np.ndarray:
+        return np.ascontiguousarray(self._ip.reconstruct_n(i0, n)[:, :self.d])
+
+    def reconstruct(self, i: int) -> np.ndarray:
+        return self.reconstruct_n(int(i), 1)[0]
+
+
+def index_factory(d: int, description: str, metric: int = METRIC_L2):
+    """faiss.index_factory (index.py:50), same signature and default metric as faiss (L2).  Only
+    the exact configuration is served: "Flat" -> IndexFlatL2 / IndexFlatIP; anything else
+    (IVF/PQ/HNSW...) is approximate and is refused rather than silently made exact or approximated."""
     if description.strip() != "Flat":
         raise RuntimeError(f"index_factory: only 'Flat' is supported by the exact B200 path, got {description!r}")
-    if metric != METRIC_INNER_PRODUCT:
-        raise RuntimeError("index_factory: only METRIC_INNER_PRODUCT is supported")
-    return IndexFlatIP(d)
+    if metric == METRIC_L2:
+        return IndexFlatL2(d)
+    if metric == METRIC_INNER_PRODUCT:
+        return IndexFlatIP(d)
+    raise RuntimeError(f"index_factory: unsupported metric {metric}")
 
 
 # faiss IndexFlat on-disk layout (faiss/impl/index_write.cpp, from the published format):
 # fourcc "IxFI", d:int32, ntotal:int64, dummy:int64 x2 (1<<20), is_trained:uint8,
 # metric_type:int32, then the raw vector as count:uint64 (number of floats) + float32 data.
-_FOURCC = b"IxFI"
+_FOURCC = {METRIC_INNER_PRODUCT: b"IxFI", METRIC_L2: b"IxF2"}
 _CHUNK_ROWS = 1 << 18
 
 
-def write_index(index: IndexFlatIP, path: str) -> None:
+def write_index(index, path: str) -> None:
     """faiss.write_index (trainer.py:245): streams the fp32 plane back to disk."""
     n, d = index.ntotal, index.d
+    metric = getattr(index, "metric_type", METRIC_INNER_PRODUCT)
     with open(path, "wb") as f:
-        f.write(_FOURCC)
-        f.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, METRIC_INNER_PRODUCT))
+        f.write(_FOURCC[metric])
+        f.write(struct.pack("<iqqqBi", d, n, 1 << 20, 1 << 20, 1, metric))
         f.write(struct.pack("<Q", n * d))
         for r0 in range(0, n, _CHUNK_ROWS):
             index.reconstruct_n(r0, min(_CHUNK_ROWS, n - r0)).tofile(f)
 
 
-def read_index(path: str, device: int | None = None) -> IndexFlatIP:
+def read_index(path: str, device: int | None = None):
     """faiss.read_index (trainer.py:257)."""
     with open(path, "rb") as f:
-        if f.read(4) != _FOURCC:
-            raise RuntimeError(f"read_index: {path} is not an IndexFlatIP file")
+        fourcc = f.read(4)
+        if fourcc not in _FOURCC.values():
+            raise RuntimeError(f"read_index: {path} is not an IndexFlatIP / IndexFlatL2 file")
         d, n, _, _, _, metric = struct.unpack("<iqqqBi", f.read(struct.calcsize("<iqqqBi")))
         (count,) = struct.unpack("<Q", f.read(8))
-        if metric != METRIC_INNER_PRODUCT or count != n * d:
+        if _FOURCC.get(metric) != fourcc or count != n * d:
             raise RuntimeError(f"read_index: unsupported header in {path}")
-        index = IndexFlatIP(d, device=device)
+        index = IndexFlatIP(d, device=device) if metric == METRIC_INNER_PRODUCT else IndexFlatL2(d, device=device)
         for r0 in range(0, n, _CHUNK_ROWS):
             rows = min(_CHUNK_ROWS, n - r0)
             buf = np.fromfile(f, dtype=np.float32, count=rows * d)

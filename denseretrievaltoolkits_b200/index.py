@@ -6,7 +6,8 @@ Same class names, constructor arguments and return conventions as the reference
     otherwise the argument is taken as the integer dimension.  `init_reps` is NOT added.
   * `.add(p_reps)` appends rows; ids are insertion order.
   * `.search(q_reps, k=1000)` returns ids only, int64 [Q,k], each row ordered by descending
-    score (the reference re-orders with np.argsort(-scores), an identity on sorted rows).
+    score (the reference re-orders with np.argsort(-scores), an identity on sorted rows; for
+    the L2 index of `FaissRetriever(reps, "Flat")` that re-ordering is applied as upstream).
   * `.batch_search(q_reps, k, batch_size, quiet=False)` returns the concatenated ids.  (As
     written upstream it raises ValueError — index.py:40 unpacks `search`'s single array into
     two names; the intended behaviour, chunked search + concatenation, is implemented.)
@@ -42,7 +43,18 @@ class BaseFaissIPRetriever:
         return self.index.search(q_reps, k)
 
     def search(self, q_reps, k: int = 1000):
-        _, indices = self.index.search(q_reps, k)
+        scores, indices = self.index.search(q_reps, k)
+        if getattr(self.index, "metric_type", faiss.METRIC_INNER_PRODUCT) != faiss.METRIC_INNER_PRODUCT:
+            # index.py:32-33 re-orders every row by argsort(-scores).  Rows of an inner-product
+            # index are already in that order; the ascending distances of the L2 index that
+            # `FaissRetriever(reps, "Flat")` holds come out farthest-first, as upstream.
+            if _is_ndarray(scores):
+                order = np.argsort(-scores, axis=1, kind="stable")
+                return np.take_along_axis(indices, order, axis=1)
+            import torch
+
+            order = torch.argsort(-scores, dim=1, stable=True)
+            return torch.gather(indices, 1, order)
         return indices
 
     def batch_search_with_scores(self, q_reps, k: int, batch_size: int, quiet: bool = False):

@@ -181,3 +181,79 @@ def torch_flat_ip_search(corpus_t, q_t, k: int, block_rows: int = 262144):
             best_i = torch.gather(best_i, 1, sel)
             best_d = d2
     return best_d, best_i
+
+
+# ---- faiss.index_factory(d, "Flat") -------------------------------------------------------------
+# `FaissRetriever.__init__` (DRT/evaluator/index.py:49-54) calls `faiss.index_factory(d,
+# factory_str)` WITHOUT a metric, and faiss' published signature is
+# `index_factory(d, description, metric=METRIC_L2)`: the string "Flat" therefore yields an
+# IndexFlatL2 (squared euclidean distances, ascending).  Restated here for the one exact string.
+METRIC_INNER_PRODUCT = 0
+METRIC_L2 = 1
+FLT_MAX = np.float32(3.4028234663852886e38)
+
+
+class IndexFlatL2:
+    """faiss.IndexFlatL2 restatement: `search` -> (D float32 [Q,k] squared L2 distances in
+    ascending order, I int64 [Q,k]); canonical tie order (distance asc, id asc); `k > ntotal`
+    pads with (+FLT_MAX, -1).  Distances are accumulated in float64 from the fp32 inputs."""
+
+    metric_type = METRIC_L2
+
+    def __init__(self, d: int):
+        self.d = int(d)
+        self.is_trained = True
+        self.verbose = False
+        self._blocks: list[np.ndarray] = []
+        self.ntotal = 0
+
+    def add(self, x: np.ndarray) -> None:
+        x = np.ascontiguousarray(x, dtype=np.float32)
+        if x.ndim != 2 or x.shape[1] != self.d:
+            raise RuntimeError(f"add: expected [n,{self.d}] float32, got {x.shape}")
+        self._blocks.append(x.copy())
+        self.ntotal += x.shape[0]
+
+    def train(self, x) -> None:
+        return None
+
+    def reset(self) -> None:
+        self._blocks, self.ntotal = [], 0
+
+    def reconstruct_n(self, i0: int, n: int) -> np.ndarray:
+        allx = np.concatenate(self._blocks) if self._blocks else np.zeros((0, self.d), np.float32)
+        return allx[i0 : i0 + n].copy()
+
+    def search(self, q: np.ndarray, k: int):
+        q = np.ascontiguousarray(q, dtype=np.float32)
+        if q.ndim != 2 or q.shape[1] != self.d:
+            raise RuntimeError(f"search: expected [nq,{self.d}] float32, got {q.shape}")
+        x = (np.concatenate(self._blocks) if self._blocks else np.zeros((0, self.d), np.float32)).astype(np.float64)
+        Q, N = q.shape[0], x.shape[0]
+        D = np.full((Q, k), FLT_MAX, dtype=np.float32)
+        I = np.full((Q, k), -1, dtype=np.int64)
+        kk = min(k, N)
+        ids = np.arange(N)
+        xn = np.einsum("ij,ij->i", x, x)
+        for r in range(Q):
+            qr = q[r].astype(np.float64)
+            dist = np.maximum(xn - 2.0 * (x @ qr) + qr @ qr, 0.0)
+            if N <= 4096:                      # small cases: the literal definition sum((q-x)^2)
+                dist = ((x - qr[None, :]) ** 2).sum(1)
+            order = np.lexsort((ids, dist))[:kk]
+            D[r, :kk] = dist[order].astype(np.float32)
+            I[r, :kk] = order
+        return D, I
+
+
+def index_factory(d: int, description: str, metric: int = METRIC_L2):
+    """faiss.index_factory for the exact string only (index.py:50)."""
+    if description.strip() != "Flat":
+        raise RuntimeError(f"oracle index_factory: only 'Flat' is restated, got {description!r}")
+    return IndexFlatL2(d) if metric == METRIC_L2 else IndexFlatIP(d)
+
+
+def flat_l2_search(corpus: np.ndarray, q: np.ndarray, k: int):
+    idx = IndexFlatL2(corpus.shape[1])
+    idx.add(corpus)
+    return idx.search(q, k)

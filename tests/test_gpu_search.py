@@ -153,7 +153,69 @@ def test_empty_index_and_errors():
 
     with pytest.raises(RuntimeError):
         faiss_compat.index_factory(768, "IVF100,PQ8")             # approximate: refused, no fallback
-    assert isinstance(faiss_compat.index_factory(768, "Flat"), faiss_compat.IndexFlatIP)
+    # faiss' signature: index_factory(d, description, metric=METRIC_L2)
+    assert isinstance(faiss_compat.index_factory(768, "Flat"), faiss_compat.IndexFlatL2)
+    assert isinstance(faiss_compat.index_factory(768, "Flat", faiss_compat.METRIC_INNER_PRODUCT), faiss_compat.IndexFlatIP)
+
+
+def _check_l2(D, I, Dr, Ir, x, q):
+    """ids identical except among distances that tie within tolerance; distances within RTOL of
+    the float64 oracle (tolerance scaled by the cancelling terms |q|^2 + |x|^2)."""
+    valid = Ir >= 0
+    np.testing.assert_array_equal(I >= 0, valid)
+    atol = RTOL * (float((q.astype(np.float64) ** 2).sum(1).max()) + float((x.astype(np.float64) ** 2).sum(1).max()))
+    np.testing.assert_allclose(D[valid], Dr[valid], rtol=RTOL, atol=atol)
+    diff = (I != Ir) & valid
+    assert np.all(np.abs(D[diff] - Dr[diff]) <= RTOL * np.abs(Dr[diff]) + atol)
+    assert (np.diff(D, axis=1) >= 0).all()                       # ascending distances
+    assert (D[~valid] == np.float32(3.4028234663852886e38)).all()
+    k = I.shape[1]
+    kk = min(k, x.shape[0])
+    assert np.mean([len(set(a[:kk]) & set(b[:kk])) / kk for a, b in zip(I, Ir)]) >= 0.999
+
+
+@pytest.mark.parametrize("n,d,k", [(20000, 768, 100), (3000, 100, 10), (5, 64, 8)])
+def test_index_flat_l2_matches_oracle(n, d, k, tmp_path):
+    """`faiss.index_factory(d, "Flat")` = IndexFlatL2 (what FaissRetriever holds, index.py:50):
+    exact squared-L2 search on the inner-product store through the norm-augmented rows."""
+    from denseretrievaltoolkits_b200 import faiss_compat
+
+    rng = np.random.default_rng(n + d)
+    x = (rng.standard_normal((n, d)) * rng.uniform(0.5, 1.5, size=(n, 1))).astype(np.float32)   # varied norms
+    q = rng.standard_normal((60, d), dtype=np.float32)
+    index = faiss_compat.index_factory(d, "Flat")
+    index.add(x[: n // 2])
+    index.add(torch.from_numpy(x[n // 2:]).cuda())
+    assert index.ntotal == n and index.d == d and index.metric_type == faiss_compat.METRIC_L2
+    D, I = index.search(q, k)
+    Dr, Ir = flat_ip.flat_l2_search(x, q, k)
+    _check_l2(D, I, Dr, Ir, x, q)
+    Dd, Id = index.search(torch.from_numpy(q).cuda(), k)
+    np.testing.assert_array_equal(Id.cpu().numpy(), I)
+    np.testing.assert_allclose(Dd.cpu().numpy(), D, rtol=1e-6, atol=1e-3)
+    np.testing.assert_array_equal(index.reconstruct_n(0, min(n, 7)), x[: min(n, 7)])
+    path = str(tmp_path / "l2.faiss")
+    faiss_compat.write_index(index, path)
+    again = faiss_compat.read_index(path)
+    assert isinstance(again, faiss_compat.IndexFlatL2)
+    D2, I2 = again.search(q, k)
+    np.testing.assert_array_equal(I2, I)
+
+
+def test_faiss_retriever_flat_matches_reference_wrapper_golden(golden_dir):
+    """The reference's FaissRetriever, run unmodified over the oracle stub, pinned the ids it
+    returns for index_factory(d, "Flat"): L2 neighbours, re-ordered by argsort(-distance)."""
+    from denseretrievaltoolkits_b200.index import FaissRetriever
+
+    g = np.load(os.path.join(golden_dir, "search_factory_flat.npz"))
+    r = FaissRetriever(g["x"], "Flat")
+    assert r.index.ntotal == 0 and r.index.verbose is True
+    r.add(g["x"])
+    ids = r.search(g["q"], int(g["k"]))
+    np.testing.assert_array_equal(ids, g["wrapper_ids"])
+    D, I = r.index.search(g["q"], int(g["k"]))
+    np.testing.assert_array_equal(I, g["I"])
+    np.testing.assert_allclose(D, g["D"], rtol=RTOL, atol=1e-3)
 
 
 def test_write_read_index_roundtrip(tmp_path):

@@ -158,3 +158,29 @@ def test_mining_filter_matches_reference_loop(golden_dir):
                                      c["num_negative"])
         kept = [int(v) for v in out[0] if v >= 0]
         assert kept == c["kept"]
+
+
+def test_l2_oracle_and_factory_golden(golden_dir):
+    """index_factory(d, "Flat") without a metric is faiss' IndexFlatL2; the golden holds what the
+    reference's FaissRetriever (index.py:47-54) returned over this oracle."""
+    g = np.load(os.path.join(golden_dir, "search_factory_flat.npz"))
+    x, q, k = g["x"], g["q"], int(g["k"])
+    assert int(g["metric"]) == flat_ip.METRIC_L2
+    idx = flat_ip.index_factory(x.shape[1], "Flat")
+    assert isinstance(idx, flat_ip.IndexFlatL2)
+    idx.add(x)
+    D, I = idx.search(q, k)
+    np.testing.assert_array_equal(I, g["I"])
+    np.testing.assert_allclose(D, g["D"], rtol=1e-6)
+    # the literal definition, float64
+    d2 = ((q[:, None, :].astype(np.float64) - x[None, :, :].astype(np.float64)) ** 2).sum(-1)
+    np.testing.assert_array_equal(I, np.argsort(d2, axis=1, kind="stable")[:, :k])
+    # the wrapper's argsort(-scores) re-order: farthest of the k first
+    ids = np.array([ind[o] for ind, o in zip(I, np.argsort(-D, kind="stable"))])
+    np.testing.assert_array_equal(ids, g["wrapper_ids"])
+    # k > ntotal pads with (+FLT_MAX, -1); IP metric still available
+    D2, I2 = flat_ip.flat_l2_search(x[:3], q[:2], 5)
+    assert (I2[:, 3:] == -1).all() and (D2[:, 3:] == flat_ip.FLT_MAX).all()
+    assert isinstance(flat_ip.index_factory(8, "Flat", flat_ip.METRIC_INNER_PRODUCT), flat_ip.IndexFlatIP)
+    with pytest.raises(RuntimeError):
+        flat_ip.index_factory(8, "IVF16,Flat")

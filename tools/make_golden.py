@@ -8,6 +8,7 @@ are produced by running the reference's own importable code on seeded inputs:
   * search_*.npz  DRT/evaluator/index.py's BaseFaissIPRetriever executed, unmodified, over a
                   faiss-shaped stub whose IndexFlatIP is oracle/flat_ip.py (faiss itself is not
                   installable here), plus a float64 brute force of the same inputs
+  * search_factory_flat.npz  FaissRetriever (index.py:47-54) unmodified over the same stub
   * mining.json   the loop of process_sample (DRT/trainer/sampler.py:73-78) restated verbatim
                   (the closure lives in a module that needs faiss at import time)
 Run:  python tools/make_golden.py        (needs /root/reference; tests never do)
@@ -139,6 +140,21 @@ def search_goldens():
     for name, c in cases.items():
         np.savez_compressed(os.path.join(OUT, f"search_{name}.npz"), **c)
         print("search", name, c["wrapper_ids"].shape, "batch_search_raises", int(c["batch_search_raises"]))
+
+    # FaissRetriever (index.py:47-54), unmodified, over the stub: index_factory(d, "Flat") without a
+    # metric is faiss' default METRIC_L2, and the inherited search() re-orders the ascending
+    # distances by argsort(-scores)
+    stub.index_factory = flat_ip.index_factory
+    from DRT.evaluator.index import FaissRetriever
+
+    r = FaissRetriever(x, "Flat")
+    assert r.index.ntotal == 0 and r.index.verbose is True
+    r.add(x)
+    ids = r.search(q, 10)
+    D, I = r.index.search(q, 10)
+    np.savez_compressed(os.path.join(OUT, "search_factory_flat.npz"), x=x, q=q, k=np.array(10), wrapper_ids=ids, D=D, I=I,
+                        metric=np.array(r.index.metric_type))
+    print("search factory_flat", ids.shape, "metric", r.index.metric_type)
 
 
 def mining_goldens():
