@@ -828,8 +828,12 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int S, long 
 }
 
 inline bool tc_shape_ok(long long M, long long N, long long K) {
-    // worth the split + launch overhead only for big problems; K' = 6K must be a multiple of 64
-    return K % 32 == 0 && (double)M * (double)N * (double)K >= 2.0e9 && M >= 128 && N >= 256;
+    // worth the split + extra launches from ~256 x 2048 x 768 up (tools/ce_bench.py); K' = 6K must be a multiple of 64
+    static const double min_work = [] {
+        const char* e = getenv("DRT_B200_CE_TC_MIN");     // tuning knob: M*N*K above which the tensor-core path runs
+        return e ? atof(e) : 3.0e8;      // measured cross-over vs the SIMT core: 256 x 2048 x 768 already wins
+    }();
+    return K % 32 == 0 && (double)M * (double)N * (double)K >= min_work && M >= 128 && N >= 256;
 }
 
 int ce_tc_setup(CeWorkspace& w) {

@@ -49,7 +49,7 @@ def test_loss_matches_reference_goldens(path):
         np.testing.assert_allclose(dy.sum(0), g["dy_colsum"], rtol=1e-3, atol=1e-4)
 
 
-@pytest.mark.parametrize("B,n,d", [(128, 8, 768), (16, 2, 768), (5, 3, 64), (33, 7, 96), (1024, 8, 768)])
+@pytest.mark.parametrize("B,n,d", [(128, 8, 768), (16, 2, 768), (5, 3, 64), (33, 7, 96), (256, 8, 768), (512, 8, 768), (1024, 8, 768)])
 def test_loss_matches_torch_fp32_and_oracle(B, n, d):
     from denseretrievaltoolkits_b200.losses import SimpleContrastiveLoss, inbatch_scores_and_loss
 

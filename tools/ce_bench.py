@@ -22,7 +22,10 @@ def timeit(fn, reps=200, warm=20):
     return e0.elapsed_time(e1) / reps * 1e3   # us
 
 
-for B, n in [(128, 8), (1024, 8), (16, 2)]:
+shapes = [(128, 8), (1024, 8), (16, 2)]
+if os.environ.get("CE_SHAPES"):
+    shapes = [tuple(int(v) for v in t.split("x")) for t in os.environ["CE_SHAPES"].split(",")]
+for B, n in shapes:
     x = torch.randn(B, 768, device=dev, requires_grad=True)
     y = torch.randn(B * n, 768, device=dev, requires_grad=True)
     tgt = torch.arange(0, B * n, n, device=dev)
