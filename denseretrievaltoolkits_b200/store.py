@@ -141,8 +141,8 @@ class ShardedCorpusStore:
     def local_depth(self, k: int) -> int:
         """Depth every shard is searched to for a global top-k.
 
-        With rows dealt to W shards independently of the queries, a shard holds Binomial(k, 1/W)
-        of a query's global top-k, so mean + 6 sigma entries per shard suffice almost surely
+        With rows dealt to W shards independently of the queries, a shard that owns a fraction p of
+        the rows holds Binomial(k, p) of a query's global top-k (p = 1/W for even shards), so mean + 6 sigma entries per shard suffice almost surely
         (k=100, W=8: 40 instead of 100; k=1000, W=8: 192) — and rescoring, the candidate
         exchange and the merge all shrink with it.  The result stays EXACT: after the merge a
         query whose global k-th score does not lie strictly above the last entry of every
@@ -151,7 +151,13 @@ class ShardedCorpusStore:
         W = self.world
         if W <= 1 or not self._reduce_depth:
             return k
-        p = 1.0 / W
+        if self._offsets is None:
+            self.finalize()
+        total = self._offsets[-1]
+        if total <= 0:
+            return k
+        # the largest shard's share of the rows (1/W for even shards); every shard uses the same depth
+        p = max(self._offsets[g + 1] - self._offsets[g] for g in range(W)) / float(total)
         kl = int(math.ceil((k * p + 6.0 * math.sqrt(k * p * (1.0 - p)) + 4.0) / 8.0) * 8)
         return min(k, max(kl, -(-k // W)))
 
