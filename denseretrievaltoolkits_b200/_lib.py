@@ -117,10 +117,20 @@ def check(status: int, what: str) -> None:
         raise RuntimeError(f"{what} failed (status {status}): {last_error()}")
 
 
+_raw_stream = None
+
+
 def current_stream_ptr(device_index: int | None = None) -> int:
     """The caller's current torch CUDA stream as a raw cudaStream_t (0 when torch has no CUDA)."""
-    import torch
+    global _raw_stream
+    if _raw_stream is None:
+        import torch
 
-    if not torch.cuda.is_available():
-        return 0
-    return int(torch.cuda.current_stream(device_index).cuda_stream)
+        if not torch.cuda.is_available():
+            return 0
+        fast = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        if fast is not None:
+            _raw_stream = lambda idx: int(fast(torch.cuda.current_device() if idx is None else idx))
+        else:
+            _raw_stream = lambda idx: int(torch.cuda.current_stream(idx).cuda_stream)
+    return _raw_stream(device_index)

@@ -22,14 +22,14 @@ _KEEP_LOGITS_BYTES = 1 << 30
 
 
 def _f32c(t: Tensor) -> Tensor:
-    t = t.detach()
+    # called inside autograd.Function.forward/backward (grad mode is off there): no detach needed
     if t.dtype is not torch.float32:
         t = t.to(torch.float32)
     return t if t.is_contiguous() else t.contiguous()
 
 
 class _InBatchCE(torch.autograd.Function):
-    """(x [B,d], y [P,d], target|None, reduction, want_logits) -> (loss, logits|empty).
+    """(x [B,d], y [P,d], target|None, reduction, want_logits) -> (loss, logits|None).
     `loss` is a 0-dim tensor for 'mean'/'sum' and [B] for 'none'."""
 
     @staticmethod
@@ -54,15 +54,17 @@ class _InBatchCE(torch.autograd.Function):
         # unless the matrix is huge; they are only RETURNED when the caller asked for them
         keep_logits = want_logits or (B * P * 4 <= _KEEP_LOGITS_BYTES and any(ctx.needs_input_grad[:2]))
         logits = torch.empty((B, P), dtype=torch.float32, device=dev) if keep_logits else None
-        lse = torch.empty((B,), dtype=torch.float32, device=dev)           # saved for backward
-        out = torch.empty((B + 1,), dtype=torch.float32, device=dev)       # per-row loss | total
+        out = torch.empty((2 * B + 1,), dtype=torch.float32, device=dev)   # per-row loss | total | lse (one allocation)
+        lse = out[B + 1:]                                                   # saved for backward
         scale = 1.0 / B if reduction == "mean" else 1.0
         stream = _lib.current_stream_ptr(dev.index)
         base = out.data_ptr()
-        _lib.check(lib.drt_inbatch_ce_fwd(
+        rc = lib.drt_inbatch_ce_fwd(
             xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if tgt is not None else None, scale,
-            logits.data_ptr() if logits is not None else None, lse.data_ptr(), base, base + 4 * B,
-            dev.index, stream), "inbatch_ce_fwd")
+            logits.data_ptr() if logits is not None else None, base + 4 * (B + 1), base, base + 4 * B,
+            dev.index, stream)
+        if rc != 0:
+            _lib.check(rc, "inbatch_ce_fwd")
         ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else lse, logits if logits is not None else lse)
         ctx.has_target = tgt is not None
         ctx.has_logits = logits is not None
@@ -70,10 +72,11 @@ class _InBatchCE(torch.autograd.Function):
         ctx.reduction = reduction
         ctx.scale = scale
         ctx.in_dtypes = (x.dtype, y.dtype)
-        ret_logits = logits if want_logits else out.new_empty(0)
-        ctx.mark_non_differentiable(ret_logits)
         loss = out[:B] if reduction == "none" else out[B]
-        return loss, ret_logits
+        if want_logits:
+            ctx.mark_non_differentiable(logits)
+            return loss, logits
+        return loss, None
 
     @staticmethod
     def backward(ctx, grad_loss: Tensor, _grad_logits):
