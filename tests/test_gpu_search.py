@@ -569,3 +569,19 @@ def test_single_query_single_row_and_k1():
     D, I = index.search(q, 1)
     Dr, Ir = flat_ip.flat_ip_search(np.concatenate([x, x2]), q, 1)
     np.testing.assert_array_equal(I, Ir)
+
+
+@pytest.mark.parametrize("nq", [5, 300])
+def test_maximum_depth_k2048(nq):
+    """k = DRT_MAX_K: k' = 2,344 candidates per query in the 16,384-entry buffer, both tile variants."""
+    rng = np.random.default_rng(2048 + nq)
+    x = rng.standard_normal((60000, 256), dtype=np.float32)
+    q = rng.standard_normal((nq, 256), dtype=np.float32)
+    index = _mk(d=256, seg_rows=1 << 14)
+    index.add(x)
+    D, I = index.search(q, 2048)
+    st = index.search_stats()
+    assert st["overflow_retries"] == 0 and st["flagged_queries"] == 0
+    Dr, Ir = flat_ip.flat_ip_search(x, q[:40], 2048)
+    _check_parity(D[:40], I[:40], Dr, Ir, 2048, 60000, scale=16.0)
+    assert (np.diff(D, axis=1) <= 0).all() and all(len(set(r)) == 2048 for r in I)
