@@ -6,12 +6,13 @@
 // mantissa bits) and contracting the six products that matter,
 //     hi·hi + hi·mid + mid·hi + mid·mid + hi·lo + lo·hi        (dropped: ≤ 2^-24 relative),
 // as ONE bf16 GEMM over a K axis of length 6K: the split kernels below lay the pieces out as
-//     A' = [ hi | hi  | mid | mid | hi | lo ]      B' = [ hi | mid | hi | mid | lo | hi ]
+//     A' = [ mid | hi | lo | hi  | mid | hi ]      B' = [ mid | lo | hi | mid | hi | hi ]
 // so A'·B'ᵀ is the sum above, accumulated in fp32 in TMEM.  bf16 x bf16 products are exact in
-// fp32; the tensor core's fp32 accumulation truncates, so over the 288 accumulation steps of a
-// 768-d contraction the error reaches ~1e-5 of the score scale (measured: 1.4e-3 abs at scale
-// 138, cuBLAS sgemm 1.9e-4) -- 10x inside the path's 1e-4 tolerance, where one plain bf16 pass
-// (~4e-3 of the scale) is 40x outside it.
+// fp32; the tensor core's fp32 accumulation truncates (~0.5 ulp of the current accumulator per
+// MMA step), which is why the segments are ordered by ascending product magnitude: the
+// accumulator stays ~2^-8 of its final size until the last (hi·hi) segment, so only K/16 steps
+// truncate at full scale.  Measured on a 768-d contraction: 1.45e-4 abs at score scale 138
+// (1e-6 relative; cuBLAS sgemm 1.9e-4; with hi·hi first 1.4e-3; one plain bf16 pass ~0.5).
 //
 // The kernel is K1's pipeline (TMA producer warp, single-thread tcgen05.mma issuer, two TMEM
 // accumulator stages, 8 epilogue warps, optional CTA pairs) with a store epilogue.
@@ -206,6 +207,10 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 }
 
 // ---- exact 3-way bf16 split of fp32 operands into the 6-segment K layout -------------------
+// The tensor core's fp32 accumulation truncates, so every MMA step costs ~0.5 ulp of the CURRENT
+// accumulator magnitude.  The six partial products are therefore laid out along K' in ascending
+// magnitude (mid*mid, hi*lo, lo*hi, hi*mid, mid*hi, hi*hi): the accumulator stays ~2^-8 of its
+// final size until the last segment, and only those K/16 steps truncate at full scale.
 __device__ __forceinline__ void split3(float x, __nv_bfloat16& hi, __nv_bfloat16& mid, __nv_bfloat16& lo) {
     hi = __float2bfloat16_rn(x);
     const float r1 = x - __bfloat162float(hi);
@@ -223,8 +228,9 @@ __global__ void split3_rows_kernel(const float* __restrict__ src, long long R, l
         __nv_bfloat16 hi, mid, lo;
         split3(src[r * lds + c], hi, mid, lo);
         __nv_bfloat16* d = dst + r * 6 * C + c;
-        if (is_b) { d[0] = hi; d[C] = mid; d[2 * C] = hi; d[3 * C] = mid; d[4 * C] = lo; d[5 * C] = hi; }
-        else      { d[0] = hi; d[C] = hi;  d[2 * C] = mid; d[3 * C] = mid; d[4 * C] = hi; d[5 * C] = lo; }
+        // segment order = ascending product magnitude: mid*mid, hi*lo, lo*hi, hi*mid, mid*hi, hi*hi
+        if (is_b) { d[0] = mid; d[C] = lo; d[2 * C] = hi; d[3 * C] = mid; d[4 * C] = hi;  d[5 * C] = hi; }
+        else      { d[0] = mid; d[C] = hi; d[2 * C] = lo; d[3 * C] = hi;  d[4 * C] = mid; d[5 * C] = hi; }
     }
 }
 
@@ -244,8 +250,8 @@ __global__ void split3_transpose_kernel(const float* __restrict__ src, long long
             __nv_bfloat16 hi, mid, lo;
             split3(tile[threadIdx.x][j], hi, mid, lo);
             __nv_bfloat16* d = dst + c * 6 * R + r;
-            if (is_b) { d[0] = hi; d[R] = mid; d[2 * R] = hi; d[3 * R] = mid; d[4 * R] = lo; d[5 * R] = hi; }
-            else      { d[0] = hi; d[R] = hi;  d[2 * R] = mid; d[3 * R] = mid; d[4 * R] = hi; d[5 * R] = lo; }
+            if (is_b) { d[0] = mid; d[R] = lo; d[2 * R] = hi; d[3 * R] = mid; d[4 * R] = hi;  d[5 * R] = hi; }
+            else      { d[0] = mid; d[R] = hi; d[2 * R] = lo; d[3 * R] = hi;  d[4 * R] = mid; d[5 * R] = hi; }
         }
     }
 }

@@ -201,11 +201,12 @@ def test_tensor_core_loss_path_is_fp32_accurate(monkeypatch):
     scale = ref64.abs().max().item()
     err_tc = (scores.double() - ref64).abs().max().item()
     err_fp32 = ((x @ y.t()).double() - ref64).abs().max().item()      # cuBLAS sgemm, the reference's arithmetic
-    # fp32 accumulation inside the tensor core truncates, so the error grows linearly with the
-    # 288 accumulation steps: ~1e-5 of the score scale -- 10x inside the path's 1e-4 tolerance and
-    # 400x better than a single bf16 pass (~4e-3 * scale); cuBLAS' sgemm error is printed beside it
+    # fp32 accumulation inside the tensor core truncates (~0.5 ulp of the accumulator per MMA step),
+    # so the six partial products are accumulated in ascending magnitude and only the last 48 steps
+    # (hi*hi) run at full scale: ~1e-6 of the score scale, on par with cuBLAS' sgemm (printed
+    # beside it) and 4000x better than a single bf16 pass (~4e-3 * scale)
     print(f"tensor-core logits: max abs err {err_tc:.3e} (scale {scale:.1f}), cuBLAS fp32 {err_fp32:.3e}")
-    assert err_tc <= 3e-5 * scale, (err_tc, err_fp32, scale)
+    assert err_tc <= 3e-6 * scale and err_tc <= 2.0 * err_fp32, (err_tc, err_fp32, scale)
     x1, y1 = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
     l1 = SimpleContrastiveLoss()(x1, y1)
     l1.backward()
@@ -216,12 +217,12 @@ def test_tensor_core_loss_path_is_fp32_accurate(monkeypatch):
     monkeypatch.delenv("DRT_B200_CE_SIMT")
     torch.testing.assert_close(l1, l2, rtol=1e-5, atol=1e-6)
     torch.testing.assert_close(loss_tc, l2.detach(), rtol=1e-5, atol=1e-6)
-    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-3, atol=1e-3 * x2.grad.abs().max().item())
-    torch.testing.assert_close(y1.grad, y2.grad, rtol=1e-3, atol=1e-3 * y2.grad.abs().max().item())
+    torch.testing.assert_close(x1.grad, x2.grad, rtol=1e-3, atol=1e-4 * x2.grad.abs().max().item())
+    torch.testing.assert_close(y1.grad, y2.grad, rtol=1e-3, atol=1e-4 * y2.grad.abs().max().item())
     # ragged large shape (M, N not multiples of the 128 / 256 tiles; K multiple of 32)
     xr, yr = x[:1000].contiguous(), y[:7968].contiguous()
     lr_, sr = inbatch_scores_and_loss(xr, yr, 7)
     ref = xr.double() @ yr.double().t()
-    assert (sr.double() - ref).abs().max().item() <= 3e-5 * ref.abs().max().item()
+    assert (sr.double() - ref).abs().max().item() <= 3e-6 * ref.abs().max().item()
     tgt = torch.arange(0, 1000 * 7, 7, device="cuda")
     torch.testing.assert_close(lr_, torch.nn.functional.cross_entropy(ref.float(), tgt), rtol=1e-4, atol=1e-5)

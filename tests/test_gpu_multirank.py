@@ -19,7 +19,16 @@ def _torchrun(script, port):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tools", script)]
     p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    lines = [json.loads(l) for l in p.stdout.splitlines() if l.startswith("{")]
+    lines, dec = [], json.JSONDecoder()
+    for l in p.stdout.splitlines():          # tolerate two ranks' objects landing on one line
+        i = l.find("{")
+        while i >= 0:
+            try:
+                obj, end = dec.raw_decode(l, i)
+            except ValueError:
+                break
+            lines.append(obj)
+            i = l.find("{", end)
     assert p.returncode == 0 and len(lines) == 2, p.stdout[-2000:] + p.stderr[-2000:]
     return lines
 

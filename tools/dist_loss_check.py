@@ -66,7 +66,8 @@ def fb_ref():
 
 
 res.update(fwdbwd_us_ours=timeit(fb_ours), fwdbwd_us_reference_formulation=timeit(fb_ref), ok=ok, world=world)
-print(json.dumps(res), flush=True)
+sys.stdout.write(json.dumps(res) + "\n")   # one write: lines of different ranks must not interleave
+sys.stdout.flush()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

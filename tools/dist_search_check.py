@@ -57,7 +57,8 @@ Dn, In = store.search(q.cpu().numpy(), 100)
 res["numpy_api_full_upload"] = bool(np.array_equal(In, If.cpu().numpy()))
 ok = ok and res["numpy_api_full_upload"]
 res["ok"] = ok
-print(json.dumps(res), flush=True)
+sys.stdout.write(json.dumps(res) + "\n")   # one write: lines of different ranks must not interleave
+sys.stdout.flush()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
