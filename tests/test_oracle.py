@@ -184,3 +184,26 @@ def test_l2_oracle_and_factory_golden(golden_dir):
     assert isinstance(flat_ip.index_factory(8, "Flat", flat_ip.METRIC_INNER_PRODUCT), flat_ip.IndexFlatIP)
     with pytest.raises(RuntimeError):
         flat_ip.index_factory(8, "IVF16,Flat")
+
+
+def test_oracles_agree_with_independent_third_party_implementations():
+    """faiss cannot be installed here, so the restatements are also checked against exact-search
+    code that is neither ours nor the reference's: torch (blocked mm + topk, the CPU path the north
+    star names when faiss is absent) for inner product, scikit-learn's brute-force
+    NearestNeighbors for squared L2."""
+    import torch
+    from sklearn.neighbors import NearestNeighbors
+
+    rng = np.random.default_rng(99)
+    x = rng.standard_normal((5000, 96)).astype(np.float32)
+    q = rng.standard_normal((40, 96)).astype(np.float32)
+    k = 25
+    D, I = flat_ip.flat_ip_search(x, q, k)
+    Dt, It = flat_ip.torch_flat_ip_search(torch.from_numpy(x), torch.from_numpy(q), k, block_rows=1024)
+    np.testing.assert_array_equal(I, It.numpy())              # continuous data: no ties
+    np.testing.assert_allclose(D, Dt.numpy(), rtol=1e-5, atol=1e-5)
+    D2, I2 = flat_ip.flat_l2_search(x, q, k)
+    nn = NearestNeighbors(n_neighbors=k, algorithm="brute", metric="sqeuclidean").fit(x.astype(np.float64))
+    Ds, Is = nn.kneighbors(q.astype(np.float64))
+    np.testing.assert_array_equal(I2, Is)
+    np.testing.assert_allclose(D2, Ds, rtol=1e-5)
