@@ -26,7 +26,9 @@ PARITY PIN STATUS: the reference ships no tests, fixtures or golden vectors for 
  (a) the mathematical definition, via a float64 brute-force cross-check,
  (b) an independent plain-C restatement (oracle/flat_ip_c.c, scalar fp32 + heap), and
  (c) the reference's own wrapper code `DRT/evaluator/index.py:16-44` executed over this oracle
-     through a faiss-shaped stub (tools/make_golden.py generated tests/golden/search_*.npz).
+     through a faiss-shaped stub (tools/make_golden.py generated tests/golden/search_*.npz), and
+ (d) third-party exact search: torch blocked mm + topk (inner product) and scikit-learn's
+     brute-force NearestNeighbors (squared L2, for the IndexFlatL2 restatement below).
 """
 from __future__ import annotations
 
