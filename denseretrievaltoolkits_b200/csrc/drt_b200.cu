@@ -643,10 +643,11 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
         float* os_dev;
         int64_t* oi_dev;
         const bool padded = s->dim_user != s->dim;
-        if (io_on_device && !padded) {
+        if (io_on_device && !padded && aligned16_ptr(q)) {
             q_dev = q + (size_t)q0 * s->dim;
         } else {
-            // host queries, or a dim that is stored zero-padded: stage into the padded workspace
+            // host queries, a dim that is stored zero-padded, or a device pointer the 16-byte
+            // vector loads cannot take: stage into the (padded) workspace
             if ((rc = s->q_f32.ensure((size_t)nb * s->dim * 4)) != DRT_OK) return rc;
             const cudaMemcpyKind kind = io_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
             if (padded) {

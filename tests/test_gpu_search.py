@@ -585,3 +585,21 @@ def test_maximum_depth_k2048(nq):
     Dr, Ir = flat_ip.flat_ip_search(x, q[:40], 2048)
     _check_parity(D[:40], I[:40], Dr, Ir, 2048, 60000, scale=16.0)
     assert (np.diff(D, axis=1) <= 0).all() and all(len(set(r)) == 2048 for r in I)
+
+
+def test_device_queries_with_4_byte_alignment():
+    """A device query pointer that is only 4-byte aligned (a view at an odd element offset) is
+    staged inside the library instead of being read with 16-byte vector loads."""
+    rng = np.random.default_rng(8)
+    x = rng.standard_normal((20000, 128), dtype=np.float32)
+    q = rng.standard_normal((50, 128), dtype=np.float32)
+    index = _mk(d=128, seg_rows=4096)
+    index.add(x)
+    flat = torch.zeros(50 * 128 + 1, device="cuda")
+    flat[1:] = torch.from_numpy(q).cuda().reshape(-1)
+    qv = flat[1:].view(50, 128)
+    assert qv.data_ptr() % 16 == 4 and qv.is_contiguous()
+    D, I = index.search(qv, 20)
+    Dh, Ih = index.search(q, 20)
+    np.testing.assert_array_equal(I.cpu().numpy(), Ih)
+    np.testing.assert_array_equal(D.cpu().numpy(), Dh)
