@@ -137,6 +137,48 @@ class ShardedCorpusStore:
             self.finalize()
         return self._offsets[-1]
 
+    # ---- persistence ------------------------------------------------------------------------
+    def save(self, directory: str) -> None:
+        """Every rank writes its own shard as a faiss IndexFlat file (`shard{g}.faiss`, readable
+        by faiss.read_index) — in parallel, instead of rank 0 writing the whole index and the
+        others reading it back (trainer.py:245,257) — plus `store.json` with the id offsets."""
+        import json
+        import os
+
+        from .faiss_compat import write_index
+
+        offs = self.finalize() if self._offsets is None else self._offsets
+        os.makedirs(directory, exist_ok=True)
+        for j, shard in enumerate(self.shards):
+            g = self.rank if self.distributed else j
+            write_index(shard, os.path.join(directory, f"shard{g}.faiss"))
+        if self.rank == 0:
+            with open(os.path.join(directory, "store.json"), "w", encoding="utf-8") as f:
+                json.dump({"d": self.d, "world": self.world, "offsets": offs}, f)
+        if self.distributed:
+            dist.barrier(group=self.group)
+
+    @classmethod
+    def load(cls, directory: str, group=None, device: Optional[int] = None, num_virtual_shards: int = 0,
+             seg_rows: int = 0) -> "ShardedCorpusStore":
+        """Inverse of `save` for the same number of shards (ranks, or virtual shards on one GPU)."""
+        import json
+        import os
+
+        from .faiss_compat import read_index
+
+        with open(os.path.join(directory, "store.json"), "r", encoding="utf-8") as f:
+            meta = json.load(f)
+        st = cls(int(meta["d"]), group=group, device=device, num_virtual_shards=num_virtual_shards, seg_rows=seg_rows)
+        if st.world != int(meta["world"]):
+            raise RuntimeError(f"store in {directory} has {meta['world']} shards, this process group has {st.world}")
+        for j in range(len(st.shards)):
+            g = st.rank if st.distributed else j
+            st.shards[j] = read_index(os.path.join(directory, f"shard{g}.faiss"), device=device)
+        if st.finalize() != [int(v) for v in meta["offsets"]]:
+            raise RuntimeError(f"store in {directory}: shard sizes do not match store.json")
+        return st
+
     # ---- search -----------------------------------------------------------------------------
     def local_depth(self, k: int) -> int:
         """Depth every shard is searched to for a global top-k.

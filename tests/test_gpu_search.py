@@ -603,3 +603,22 @@ def test_device_queries_with_4_byte_alignment():
     Dh, Ih = index.search(q, 20)
     np.testing.assert_array_equal(I.cpu().numpy(), Ih)
     np.testing.assert_array_equal(D.cpu().numpy(), Dh)
+
+
+def test_sharded_store_save_and_load(tmp_path):
+    from denseretrievaltoolkits_b200.store import ShardedCorpusStore
+
+    rng = np.random.default_rng(14)
+    x = rng.standard_normal((30000, 128), dtype=np.float32)
+    q = rng.standard_normal((40, 128), dtype=np.float32)
+    st = ShardedCorpusStore(128, num_virtual_shards=4, device=0, seg_rows=4096)
+    st.add_split(x)
+    D, I = st.search(q, 50)
+    st.save(str(tmp_path / "store"))
+    again = ShardedCorpusStore.load(str(tmp_path / "store"), num_virtual_shards=4, device=0, seg_rows=4096)
+    assert again.ntotal == 30000 and again._offsets == st._offsets
+    D2, I2 = again.search(q, 50)
+    np.testing.assert_array_equal(I2, I)
+    np.testing.assert_array_equal(D2, D)
+    with pytest.raises(RuntimeError):
+        ShardedCorpusStore.load(str(tmp_path / "store"), num_virtual_shards=2, device=0)
