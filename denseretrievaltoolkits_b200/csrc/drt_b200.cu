@@ -225,8 +225,21 @@ struct Chunk { int seg; int64_t row0, row1; };   // rows relative to the segment
 std::vector<Chunk> plan_chunks(int64_t ntotal, int64_t seg_rows, int cap, int keep, int attempt) {
     std::vector<Chunk> out;
     std::vector<int64_t> bounds;
-    const int64_t first = std::max<int64_t>(256, (cap / 2) / 256 * 256);
-    int64_t growth = std::max<int64_t>(2, std::min<int64_t>(8, 1 + (cap - keep) / (2 * (int64_t)keep)));
+    // Every row of the first chunk is admitted (thresholds start at -FLT_MAX), which costs the
+    // epilogue's slow path per row: keep it at ~4 k' rows (enough for a k'-th score to exist).
+    // Later chunks grow by up to 16x: expected admissions (growth-1) k' stay below half the buffer.
+    int64_t first = std::max<int64_t>(256, (cap / 2) / 256 * 256);
+    int64_t growth = std::max<int64_t>(2, std::min<int64_t>(16, 1 + (cap - keep) / (2 * (int64_t)keep)));
+    if (attempt == 0) {
+        // smallest first chunk (>= ~4 k') that still reaches the end of the first segment in as
+        // few growth steps as the largest admissible one (cap / 2) would
+        const int64_t target = std::min<int64_t>(ntotal, seg_rows);
+        int64_t reach = first, gpow = 1;
+        while (reach < target) { reach *= growth; gpow *= growth; }
+        const int64_t need = ((target + gpow - 1) / gpow + 255) / 256 * 256;
+        const int64_t lower = (4 * (int64_t)keep + 255) / 256 * 256;
+        first = std::min<int64_t>(first, std::max<int64_t>(need, lower));
+    }
     if (attempt == 1) growth = 2;
     const int64_t fixed = std::max<int64_t>(256, ((int64_t)(cap - keep)) / 256 * 256);
     int64_t b = 0;
@@ -236,6 +249,9 @@ std::vector<Chunk> plan_chunks(int64_t ntotal, int64_t seg_rows, int cap, int ke
         else if (attempt >= 2) nb = b + fixed;
         else nb = b * growth;
         nb = std::min(nb, ntotal);
+        // a chunk that starts inside a segment ends at that segment's end at the latest (no
+        // sliver launches behind the boundary); later chunks are whole segments
+        if (b % seg_rows != 0) nb = std::min(nb, (b / seg_rows + 1) * seg_rows);
         // split at segment boundaries
         int64_t a = b;
         while (a < nb) {
