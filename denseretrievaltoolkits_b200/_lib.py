@@ -25,6 +25,7 @@ SYMBOLS = [
     "drt_store_create", "drt_store_destroy", "drt_store_add", "drt_store_ntotal", "drt_store_dim",
     "drt_store_device", "drt_store_reset", "drt_store_reconstruct",
     "drt_search", "drt_search_stats", "drt_plan_params", "drt_plan_chunks", "drt_merge_topk",
+    "drt_merge_topk_peers",
     "drt_inbatch_ce_fwd", "drt_inbatch_ce_bwd", "drt_filter_negatives",
 ]
 
@@ -93,6 +94,8 @@ def load() -> ctypes.CDLL:
     lib.drt_plan_chunks.argtypes = [c_int64, c_int64, c_int, c_int, i64p, c_int]
     lib.drt_merge_topk.argtypes = [c_int, c_void_p, c_void_p, c_int64, c_int, c_int, c_void_p,
                                    c_void_p, c_uint32, c_int, c_void_p]
+    lib.drt_merge_topk_peers.argtypes = [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int64, c_int, c_int,
+                                         POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_void_p]
     lib.drt_inbatch_ce_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                        c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]

@@ -767,6 +767,32 @@ int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t
     return DRT_OK;
 }
 
+int drt_merge_topk_peers(int n_lists, const float* const* scores, const int64_t* const* ids, int64_t q_begin,
+                         int64_t q_count, int k_in, int k_out, float* const* out_scores, int64_t* const* out_ids,
+                         uint8_t* const* truncated, int device, void* stream) {
+    if (n_lists <= 0 || n_lists > 16 || q_begin < 0 || q_count < 0 || k_in <= 0 || k_out <= 0)
+        return fail(DRT_E_INVALID, "bad peer-merge shape");
+    if (!scores || !ids || !out_scores || !out_ids || !truncated) return fail(DRT_E_INVALID, "NULL pointer table");
+    if ((int64_t)n_lists * k_in > 8192 || k_out > 4096) return fail(DRT_E_UNSUPPORTED, "peer merge of %d x %d entries is too large", n_lists, k_in);
+    if (k_out > n_lists * k_in) return fail(DRT_E_INVALID, "k_out=%d exceeds the %d merged entries", k_out, n_lists * k_in);
+    if (q_count == 0) return DRT_OK;
+    int rc = check_device(device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(device);
+    drt::PeerPtrs p;
+    for (int i = 0; i < n_lists; ++i) {
+        if (!scores[i] || !ids[i] || !out_scores[i] || !out_ids[i] || !truncated[i]) return fail(DRT_E_INVALID, "NULL peer pointer %d", i);
+        p.scores[i] = scores[i]; p.ids[i] = (const long long*)ids[i];
+        p.out_scores[i] = out_scores[i]; p.out_ids[i] = (long long*)out_ids[i]; p.truncated[i] = truncated[i];
+    }
+    for (int i = n_lists; i < 16; ++i) { p.scores[i] = nullptr; p.ids[i] = nullptr; p.out_scores[i] = nullptr; p.out_ids[i] = nullptr; p.truncated[i] = nullptr; }
+    const size_t smem = ((size_t)n_lists * k_in + (size_t)k_out) * 12;
+    CUDA_TRY(cudaFuncSetAttribute(drt::merge_sorted_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 4096) * 12));
+    drt::merge_sorted_peers_kernel<<<(unsigned)q_count, 256, smem, (cudaStream_t)stream>>>(p, n_lists, (long long)q_begin, k_in, k_out);
+    CUDA_TRY(cudaGetLastError());
+    return DRT_OK;
+}
+
 // ---- in-batch CE ----------------------------------------------------------------------------
 namespace {
 struct CeWorkspace {

@@ -400,6 +400,80 @@ merge_sorted_kernel(int G, const float* scores, const long long* ids, long long 
     }
 }
 
+// K3 over peer memory: the candidate exchange and the merge as ONE kernel.  Every rank keeps its
+// [Q, k_in] lists in a buffer that is mapped into all peers (NVLink / NVSwitch).  The CTA of query
+// q reads the G lists of q straight from the G peers (P2P loads), merges them by rank as above,
+// and stores the merged row — and the "a shard list was cut short" flag of the reduced-depth
+// check — into EVERY peer's result buffer (P2P stores), so no all-gather precedes or follows.
+// Rank r launches the queries of its own slice; the caller brackets the launch with two
+// cross-rank barriers (lists complete before / results complete after).
+struct PeerPtrs {
+    const float* scores[16];
+    const long long* ids[16];
+    float* out_scores[16];
+    long long* out_ids[16];
+    unsigned char* truncated[16];
+};
+
+__global__ void __launch_bounds__(256)
+merge_sorted_peers_kernel(PeerPtrs p, int G, long long q_begin, int k_in, int k_out) {
+    extern __shared__ uint64_t s_raw[];
+    const long long q = q_begin + blockIdx.x;
+    const int n = G * k_in;
+    long long* s_id = reinterpret_cast<long long*>(s_raw);
+    long long* s_oid = s_id + n;
+    float* s_sc = reinterpret_cast<float*>(s_oid + k_out);
+    float* s_osc = s_sc + n;
+    __shared__ int s_valid, s_trunc;
+    if (threadIdx.x == 0) { s_valid = 0; s_trunc = 0; }
+    for (int i = threadIdx.x; i < k_out; i += blockDim.x) { s_osc[i] = -FLT_MAX; s_oid[i] = -1; }
+    __syncthreads();
+    int local_valid = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int g = i / k_in, j = i - g * k_in;
+        const size_t o = static_cast<size_t>(q) * k_in + j;
+        float sc = p.scores[g][o];
+        long long id = p.ids[g][o];
+        if (id < 0 || !(sc > -FLT_MAX)) { id = -1; sc = -FLT_MAX; } else ++local_valid;
+        s_id[i] = id; s_sc[i] = sc;
+    }
+    if (local_valid) atomicAdd(&s_valid, local_valid);
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const long long id = s_id[i];
+        if (id < 0) continue;
+        const float sc = s_sc[i];
+        const int g = i / k_in;
+        int rank = i - g * k_in;
+        for (int h = 0; h < G; ++h) {
+            if (h == g) continue;
+            int lo = 0, hi = k_in;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                const long long im = s_id[h * k_in + mid];
+                if (im >= 0 && merge_precedes(s_sc[h * k_in + mid], im, sc, id)) lo = mid + 1; else hi = mid;
+            }
+            rank += lo;
+        }
+        if (rank < k_out) { s_osc[rank] = sc; s_oid[rank] = id; }
+    }
+    __syncthreads();
+    // a full list whose last score is not strictly below the merged k_out-th may hold more rows
+    const float kth = s_osc[k_out - 1];
+    if (threadIdx.x < G) {
+        const float last = s_sc[threadIdx.x * k_in + k_in - 1];
+        if (s_id[threadIdx.x * k_in + k_in - 1] >= 0 && last >= kth) s_trunc = 1;
+    }
+    __syncthreads();
+    const unsigned char tr = static_cast<unsigned char>(s_trunc);
+    for (int g = 0; g < G; ++g) {
+        float* os = p.out_scores[g] + static_cast<size_t>(q) * k_out;
+        long long* oi = p.out_ids[g] + static_cast<size_t>(q) * k_out;
+        for (int i = threadIdx.x; i < k_out; i += blockDim.x) { os[i] = s_osc[i]; oi[i] = s_oid[i]; }
+        if (threadIdx.x == 0) p.truncated[g][q] = tr;
+    }
+}
+
 // Mining filter (process_sample, DRT/trainer/sampler.py:69-80): one warp per query, ballot
 // compaction keeps rank order.
 __global__ void filter_negatives_kernel(const long long* ids, long long nq, int k,

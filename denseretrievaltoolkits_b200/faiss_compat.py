@@ -98,7 +98,9 @@ class IndexFlatIP:
                                            _lib.current_stream_ptr(self._device)), "add")
 
     # ---- search -----------------------------------------------------------------------------
-    def search(self, x, k: int, *, id_offset: int = 0, flags: int = 0):
+    def search(self, x, k: int, *, id_offset: int = 0, flags: int = 0, out=None):
+        """`out=(D, I)`: preallocated contiguous CUDA tensors [nq,k] float32 / int64 the results
+        are written into (device queries only; used by the peer-memory exchange of store.py)."""
         k = int(k)
         if k <= 0:
             raise RuntimeError(f"search: k must be positive, got {k}")
@@ -111,8 +113,15 @@ class IndexFlatIP:
                 raise RuntimeError("search: queries and store are on different devices")
             x = x.detach().to(torch.float32).contiguous()
             nq = x.shape[0]
-            D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
-            I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
+            if out is not None:
+                D, I = out
+                if (tuple(D.shape) != (nq, k) or tuple(I.shape) != (nq, k) or D.dtype is not torch.float32
+                        or I.dtype is not torch.int64 or not D.is_contiguous() or not I.is_contiguous()
+                        or D.device != x.device or I.device != x.device):
+                    raise RuntimeError("search: out=(D, I) must be contiguous CUDA [nq,k] float32 / int64 tensors")
+            else:
+                D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
+                I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
             _lib.check(self._lib.drt_search(self._h, x.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), 1,
                                             int(id_offset), int(flags),
                                             _lib.current_stream_ptr(self._device)), "search")

@@ -67,6 +67,70 @@ def _to_host(dev, *tensors):
     return tuple(o.numpy() for o in outs)
 
 
+class _PeerExchange:
+    """Candidate exchange + merge as one kernel over peer-mapped memory (`drt_merge_topk_peers`).
+
+    One symmetric buffer per rank (torch symmetric memory: the same allocation mapped into every
+    peer over NVLink / NVSwitch) holds this rank's [Q,kl] candidate lists — the local search
+    writes them there directly — and the [Q,k] result.  After a cross-rank barrier rank r merges
+    the queries of its slice reading all W lists from the peers and stores the merged rows into
+    every peer's result region; a second barrier completes the step.  No all-gather, no
+    all-to-all, and each rank merges Q/W queries."""
+
+    def __init__(self, group, device: int, rank: int, world: int):
+        import torch.distributed._symmetric_memory as symm_mem
+
+        self._symm = symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.device = torch.device("cuda", device)
+        self.rank, self.world = rank, world
+        self.buf = None
+        self.hdl = None
+        self.cap = 0
+
+    @staticmethod
+    def _layout(Q: int, kl: int, k: int):
+        al = lambda n: (n + 255) // 256 * 256
+        sizes = [Q * kl * 4, Q * kl * 8, Q * k * 4, Q * k * 8, Q]
+        offs, o = [], 0
+        for n in sizes:
+            offs.append(o)
+            o += al(n)
+        return offs, o
+
+    def views(self, Q: int, kl: int, k: int):
+        offs, total = self._layout(Q, kl, k)
+        if total > self.cap:                                   # collective: every rank sees the same shapes
+            cap = max(total + total // 4, 1 << 20)
+            self.buf = self._symm.empty(cap, dtype=torch.uint8, device=self.device)
+            self.hdl = self._symm.rendezvous(self.buf, self.group)
+            self.cap = cap
+        b = self.buf
+        cD = b[offs[0]:offs[0] + Q * kl * 4].view(torch.float32).view(Q, kl)
+        cI = b[offs[1]:offs[1] + Q * kl * 8].view(torch.int64).view(Q, kl)
+        oD = b[offs[2]:offs[2] + Q * k * 4].view(torch.float32).view(Q, k)
+        oI = b[offs[3]:offs[3] + Q * k * 8].view(torch.int64).view(Q, k)
+        bad = b[offs[4]:offs[4] + Q]
+        return (cD, cI, oD, oI, bad), offs
+
+    def merge(self, offs, Q: int, kl: int, k: int):
+        """Barrier, merge my query slice from the peers' lists into everyone's result, barrier."""
+        import ctypes
+
+        lib = _lib.load()
+        W = self.world
+        bases = [int(p) for p in self.hdl.buffer_ptrs]
+        arr = lambda off: (ctypes.c_void_p * W)(*[b + off for b in bases])
+        per = -(-Q // W)
+        q0 = min(self.rank * per, Q)
+        qn = max(0, min(per, Q - q0))
+        self.hdl.barrier(channel=0)
+        _lib.check(lib.drt_merge_topk_peers(W, arr(offs[0]), arr(offs[1]), q0, qn, kl, k, arr(offs[2]), arr(offs[3]),
+                                            arr(offs[4]), self.device.index, _lib.current_stream_ptr(self.device.index)),
+                   "merge_topk_peers")
+        self.hdl.barrier(channel=0)
+
+
 def shard_offsets(counts) -> list[int]:
     """Global id of each shard's first row, rank-major (exclusive prefix sum) + total."""
     off = [0]
@@ -95,6 +159,7 @@ class ShardedCorpusStore:
         self._offsets: Optional[list[int]] = None
         self._next_virtual = 0
         self._reduce_depth = True
+        self._peer = None            # _PeerExchange | False (disabled) | None (not decided yet)
         self.last_search = {}
 
     # ---- ingest -----------------------------------------------------------------------------
@@ -242,9 +307,28 @@ class ShardedCorpusStore:
             return Dm.cpu().numpy(), Im.cpu().numpy()
         return Dm, Im
 
+    # DRT_B200_PEER_EXCHANGE=1: exchange + merge as one kernel over peer-mapped memory instead of
+    # NCCL all-gather / all-to-all + merge (needs torch symmetric memory on an NVLink box)
+    def _peer_ok(self, q, kl: int, k: int) -> bool:
+        if self._peer is False or not torch.is_tensor(q) or not q.is_cuda or q.shape[0] == 0:
+            return False
+        if self._peer is None:
+            import os
+
+            self._peer = False
+            if os.environ.get("DRT_B200_PEER_EXCHANGE", "0") == "1" and self.world <= 16 and dist.get_backend(self.group) == "nccl":
+                self._peer = _PeerExchange(self.group, self.shards[0].device, self.rank, self.world)
+        return self._peer is not False and self.world * kl <= 8192 and k <= 4096 and k <= self.world * kl
+
     def _search_merged(self, q, k: int, kl: int, flags: int):
         """Depth-kl search of every shard, candidate exchange, merge to depth k.
         Returns torch (D [Q,k], I [Q,k], truncated-mask [Q] or None when kl == k)."""
+        if self.distributed and self._peer_ok(q, kl, k):
+            (cD, cI, oD, oI, bad), offs = self._peer.views(q.shape[0], kl, k)
+            self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags, out=(cD, cI))
+            self._peer.merge(offs, q.shape[0], kl, k)
+            # the result region is reused by the next search: hand out copies
+            return oD.clone(), oI.clone(), (bad.bool() if kl < k else None)
         if self.distributed:
             D, I = self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags)
             if isinstance(D, np.ndarray):

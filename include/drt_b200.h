@@ -122,6 +122,20 @@ int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t
                    int k_out, float* out_scores, int64_t* out_ids, uint32_t flags, int device,
                    void* stream);
 
+/* The candidate exchange and the merge as ONE kernel over peer-mapped memory (row-sharded store,
+ * one rank per GPU on NVLink / NVSwitch): list g is read from rank g's buffer, laid out
+ * [nq][k_in] (ordered, id-disjoint lists as for DRT_MERGE_SORTED_UNIQUE); the merged rows of
+ * queries [q_begin, q_begin + q_count) and a per-query flag "some full list's last score is not
+ * strictly below the merged k_out-th" (the exactness check of a reduced per-shard depth) are
+ * stored into EVERY rank's out_scores[g] / out_ids[g] ([nq][k_out]) / truncated[g] ([nq]).
+ * The pointer tables are host arrays of n_lists (<= 16) device pointers valid on `device`.
+ * The caller provides the cross-rank barriers before (lists complete) and after (results
+ * complete).  Replaces all-gather + drt_merge_topk of store.py's NCCL path. */
+int drt_merge_topk_peers(int n_lists, const float* const* scores, const int64_t* const* ids,
+                         int64_t q_begin, int64_t q_count, int k_in, int k_out,
+                         float* const* out_scores, int64_t* const* out_ids,
+                         uint8_t* const* truncated, int device, void* stream);
+
 /* ---- in-batch-negative loss ----------------------------------------------------------------
  * SimpleContrastiveLoss.forward (DRT/trainer/losses.py:11-17) and the loss block of
  * DRModel.forward (DRT/model/biencoder.py:107-116): logits = x·yᵀ (fp32), cross entropy against

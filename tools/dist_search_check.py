@@ -56,6 +56,38 @@ store.SLICE_UPLOAD_MIN_BYTES = 1 << 62                    # whole-batch upload o
 Dn, In = store.search(q.cpu().numpy(), 100)
 res["numpy_api_full_upload"] = bool(np.array_equal(In, If.cpu().numpy()))
 ok = ok and res["numpy_api_full_upload"]
+# exchange + merge as one kernel over peer-mapped memory (torch symmetric memory)
+try:
+    os.environ["DRT_B200_PEER_EXCHANGE"] = "1"
+    store.A2A_MIN_ENTRIES, store.A2A_MIN_WORLD, store.SLICE_UPLOAD_MIN_BYTES = 1 << 20, 4, 1 << 20
+    peer = ShardedCorpusStore(d, device=lr, seg_rows=1 << 15)
+    peer.add(x[bounds[rank]:bounds[rank + 1]])
+    peer.finalize()
+    for k in (100, 1000):
+        Df, If = full.search(q, k)
+        D, I = peer.search(q, k)
+        same = bool(torch.equal(I, If) and torch.equal(D, Df))
+        res[f"k{k}_peer_exchange"] = same and peer._peer not in (None, False)
+        ok = ok and res[f"k{k}_peer_exchange"]
+    Dn, In = peer.search(q.cpu().numpy()[:997], 100)
+    res["peer_numpy_ragged"] = bool(np.array_equal(In, full.search(q, 100)[1].cpu().numpy()[:997]))
+    ok = ok and res["peer_numpy_ragged"]
+
+    def timeit(st, reps=30):
+        for _ in range(5):
+            st.search(q, 100)
+        torch.cuda.synchronize(); dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            st.search(q, 100)
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3
+
+    res["us_nccl"], res["us_peer"] = round(timeit(store), 1), round(timeit(peer), 1)
+except Exception as e:  # symmetric memory unavailable on this box
+    res["peer_exchange_error"] = repr(e)[:300]
+    ok = False
 res["ok"] = ok
 sys.stdout.write(json.dumps(res) + "\n")   # one write: lines of different ranks must not interleave
 sys.stdout.flush()
