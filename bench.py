@@ -337,6 +337,9 @@ def main():
                        else f"custom: {nq} queries x {n}x{DIM}, k={k}",
                        "nq": nq, "n": n, "dim": DIM, "k": k, "sharding": f"rows/{world}",
                        "shard_depth": store.last_search.get("local_depth") if store is not None else k,
+                       "exchange": (None if store is None else
+                                    "one kernel over peer-mapped memory (drt_merge_topk_peers)" if store._peer not in (None, False)
+                                    else "NCCL all-gather + merge kernel"),
                        "l2": "inputs larger than L2 (13.5 GB bf16 corpus streamed per step); no flush",
                        "ctas_per_tile": stats["ctas_per_tile"], "kprime": stats["kprime"],
                        "corpus_chunks": stats["chunks"], "store_build_s": build_s},

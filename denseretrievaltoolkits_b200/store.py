@@ -101,6 +101,9 @@ class _PeerExchange:
     def views(self, Q: int, kl: int, k: int):
         offs, total = self._layout(Q, kl, k)
         if total > self.cap:                                   # collective: every rank sees the same shapes
+            # everything queued on this rank — including the trailing barrier of the previous
+            # search, i.e. every peer's reads of the old buffer — is done before it is dropped
+            torch.cuda.current_stream(self.device).synchronize()
             cap = max(total + total // 4, 1 << 20)
             self.buf = self._symm.empty(cap, dtype=torch.uint8, device=self.device)
             self.hdl = self._symm.rendezvous(self.buf, self.group)
@@ -307,8 +310,10 @@ class ShardedCorpusStore:
             return Dm.cpu().numpy(), Im.cpu().numpy()
         return Dm, Im
 
-    # DRT_B200_PEER_EXCHANGE=1: exchange + merge as one kernel over peer-mapped memory instead of
-    # NCCL all-gather / all-to-all + merge (needs torch symmetric memory on an NVLink box)
+    # Exchange + merge as one kernel over peer-mapped memory (torch symmetric memory over NVLink /
+    # NVSwitch) instead of NCCL all-gather / all-to-all + merge.  Default on for NCCL groups of up
+    # to 16 ranks; DRT_B200_PEER_EXCHANGE=0 selects the NCCL path, and so does a box on which the
+    # symmetric allocation cannot be set up (the ranks agree on that with one all-reduce).
     def _peer_ok(self, q, kl: int, k: int) -> bool:
         if self._peer is False or not torch.is_tensor(q) or not q.is_cuda or q.shape[0] == 0:
             return False
@@ -316,8 +321,17 @@ class ShardedCorpusStore:
             import os
 
             self._peer = False
-            if os.environ.get("DRT_B200_PEER_EXCHANGE", "0") == "1" and self.world <= 16 and dist.get_backend(self.group) == "nccl":
-                self._peer = _PeerExchange(self.group, self.shards[0].device, self.rank, self.world)
+            if os.environ.get("DRT_B200_PEER_EXCHANGE", "1") != "0" and 1 < self.world <= 16 and dist.get_backend(self.group) == "nccl":
+                peer, ok = None, 1
+                try:
+                    peer = _PeerExchange(self.group, self.shards[0].device, self.rank, self.world)
+                    peer.views(1, 1, 1)                                    # first rendezvous
+                except Exception:
+                    ok = 0
+                flag = torch.tensor([ok], dtype=torch.int32, device=q.device)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+                if int(flag.item()) == 1:
+                    self._peer = peer
         return self._peer is not False and self.world * kl <= 8192 and k <= 4096 and k <= self.world * kl
 
     def _search_merged(self, q, k: int, kl: int, flags: int):

@@ -27,6 +27,7 @@ full = faiss_compat.IndexFlatIP(d, device=lr, seg_rows=1 << 16)
 full.add(x)
 bounds = np.linspace(0, n, world + 1).astype(int)
 bounds[1:-1] += np.arange(1, world) * 37                  # uneven shards
+os.environ["DRT_B200_PEER_EXCHANGE"] = "0"                 # this store: the NCCL exchange modes
 store = ShardedCorpusStore(d, device=lr, seg_rows=1 << 15)
 store.add(x[bounds[rank]:bounds[rank + 1]])
 offs = store.finalize()
