@@ -132,3 +132,42 @@ def test_faiss_compat_index_file_layout(tmp_path):
     (count,) = struct.unpack("<Q", raw[37:45])
     assert count == 640 and len(raw) == 45 + 640 * 4
     np.testing.assert_array_equal(np.frombuffer(raw[45:], np.float32), Fake.rows.ravel())
+
+
+def test_shard_depth_rule_and_peer_buffer_layout():
+    """Host logic of the sharded store: mean + 6 sigma per-shard depth from the largest shard's row
+    share, and the symmetric-buffer layout of the peer-memory exchange (256-byte aligned regions)."""
+    from denseretrievaltoolkits_b200.store import ShardedCorpusStore, _PeerExchange
+
+    class _Fake:
+        device = None
+
+        def __init__(self):
+            self.ntotal = 0
+
+        def add(self, x):
+            self.ntotal += len(x)
+
+    def store(sizes):
+        st = ShardedCorpusStore(8, num_virtual_shards=len(sizes), index_factory=_Fake)
+        for g, n in enumerate(sizes):
+            st.add(np.zeros((n, 8), np.float32), shard=g)
+        st.finalize()
+        return st
+
+    even8 = store([1000] * 8)
+    assert [even8.local_depth(k) for k in (10, 100, 200, 1000, 2048)] == [10, 40, 64, 192, 352]
+    assert store([500, 500]).local_depth(100) == 88 and store([250] * 4).local_depth(100) == 56
+    assert store([1000]).local_depth(100) == 100                      # one shard: full depth
+    skew = store([5700, 4300])                                        # the larger shard owns 57 %
+    assert skew.local_depth(200) == 168 and skew.local_depth(20) == 20
+    for k in (1, 7, 100, 1000):                                       # always enough entries for a global top-k
+        for st in (even8, skew):
+            kl = st.local_depth(k)
+            assert kl <= k and kl * st.world >= k
+    even8._reduce_depth = False
+    assert even8.local_depth(100) == 100
+    offs, total = _PeerExchange._layout(6980, 40, 100)
+    sizes = [6980 * 40 * 4, 6980 * 40 * 8, 6980 * 100 * 4, 6980 * 100 * 8, 6980]
+    assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and total % 256 == 0
+    assert all(offs[i] + sizes[i] <= offs[i + 1] for i in range(4)) and offs[4] + sizes[4] <= total
