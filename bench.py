@@ -8,7 +8,9 @@ A "step" is one pass of the hot path over one query batch: every query of the ba
 whole corpus, top-k out.  Workload at N = 1: the headline shape of BASELINE.json / SURVEY.md
 §8d — 6,980 queries x 8.8M x 768 corpus, k = 100 (cfg2's shape at the metric's depth).  At
 N > 1 the same corpus is row-sharded over the ranks ("scaling": "strong"): every rank scans its
-shard for all queries, the [Q,k] candidates are exchanged with one NCCL all-gather and merged.
+shard for all queries (to the reduced per-shard depth, `config.shard_depth`), then the candidate
+lists are exchanged and merged by one kernel over peer-mapped memory (`config.exchange`; NCCL
+all-gather + merge kernel when DRT_B200_PEER_EXCHANGE=0).
 Synthetic data: corpus rows iid N(0,1) generated on the device per 2^20-row chunk with seed
 1234 + chunk index (identical corpus for every N), queries N(0,1) seed 4321.  The corpus
 (13.5 GB bf16 streamed per pass) is far larger than L2, so no explicit L2 flush is needed.
