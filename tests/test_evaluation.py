@@ -33,7 +33,15 @@ def test_hits_matrix_equals_per_pair_calls_and_uses_pool():
     ids = [list(range(len(texts))) for _ in answers]
     want = np.array([[ev.has_answers(t, a) for t in texts] for a in answers], dtype=np.int8)
     np.testing.assert_array_equal(ev.hits_matrix(docs, answers, doc_ids=ids, workers=1), want)
-    np.testing.assert_array_equal(ev.hits_matrix(docs * 4, answers * 4, doc_ids=ids * 4, workers=2), np.tile(want, (4, 1)))
+    ev._POOL_MIN_DOCS = 0                                   # force the (persistent) process pool on this small case
+    try:
+        np.testing.assert_array_equal(ev.hits_matrix(docs * 4, answers * 4, doc_ids=ids * 4, workers=2), np.tile(want, (4, 1)))
+        first = ev._POOL_STATE["pool"]
+        np.testing.assert_array_equal(ev.hits_matrix(docs * 4, answers * 4, doc_ids=ids * 4, workers=2), np.tile(want, (4, 1)))
+        assert first is not None and ev._POOL_STATE["pool"] is first        # the pool is reused between calls
+    finally:
+        ev._POOL_MIN_DOCS = 20000
+        ev.shutdown_pool()
     np.testing.assert_array_equal(ev.hits_matrix(docs, answers, workers=1), want)     # no doc-id cache
 
 
