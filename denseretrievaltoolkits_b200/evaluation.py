@@ -35,13 +35,15 @@ except ImportError as e:  # pragma: no cover
     raise ImportError("denseretrievaltoolkits_b200.evaluation needs the `regex` package (as DRT.evaluator.nq_eval does)") from e
 import re as _re
 
-_TOKEN = _regex.compile(r"([\p{L}\p{N}\p{M}]+)|([^\p{Z}\p{C}])",
+# SimpleTokenizer's pattern (nq_eval.py:147-160) without its two capture groups — the matches
+# are the same, and a group-free pattern lets `findall` return the tokens from C
+_TOKEN = _regex.compile(r"[\p{L}\p{N}\p{M}]+|[^\p{Z}\p{C}]",
                         flags=_regex.IGNORECASE + _regex.UNICODE + _regex.MULTILINE)
 
 
 def tokenize_uncased(text: str) -> List[str]:
     """SimpleTokenizer.tokenize(text).words(uncased=True) (nq_eval.py:145-185)."""
-    return [m.group().lower() for m in _TOKEN.finditer(text)]
+    return [w.lower() for w in _TOKEN.findall(text)]
 
 
 def _normalize(text: str) -> str:
