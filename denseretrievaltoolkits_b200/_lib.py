@@ -23,7 +23,7 @@ _SRC = os.path.join(_PKG_DIR, "csrc", "drt_b200.cu")
 SYMBOLS = [
     "drt_abi_version", "drt_last_error", "drt_device_count",
     "drt_store_create", "drt_store_destroy", "drt_store_add", "drt_store_ntotal", "drt_store_dim",
-    "drt_store_device", "drt_store_reset", "drt_store_reconstruct",
+    "drt_store_device", "drt_store_reset", "drt_store_reconstruct", "drt_store_set_exact_tail",
     "drt_search", "drt_search_stats", "drt_plan_params", "drt_plan_chunks", "drt_merge_topk",
     "drt_merge_topk_peers",
     "drt_inbatch_ce_fwd", "drt_inbatch_ce_bwd", "drt_filter_negatives",
@@ -86,6 +86,7 @@ def load() -> ctypes.CDLL:
     lib.drt_store_dim.argtypes = [c_void_p]
     lib.drt_store_device.argtypes = [c_void_p]
     lib.drt_store_reset.argtypes = [c_void_p]
+    lib.drt_store_set_exact_tail.argtypes = [c_void_p, c_int]
     lib.drt_store_reconstruct.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]
     lib.drt_search.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                                c_int64, c_uint32, c_void_p]

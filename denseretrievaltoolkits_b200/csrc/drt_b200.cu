@@ -8,6 +8,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -136,17 +137,31 @@ inline bool aligned16_ptr(const void* p) { return (reinterpret_cast<uintptr_t>(p
 }  // namespace
 
 // =============================================================================================
+// One corpus segment: row r of the store lives in segment r / seg_rows.  Every segment but the
+// last holds exactly seg_rows rows; the last one is allocated for the rows it has to hold and
+// grows geometrically up to seg_rows (a 10-row index does not pin a 2^20-row segment).
+struct Segment {
+    float* f32 = nullptr;           // [cap][dim] exact plane (rescoring, reconstruct, write_index)
+    void* bf16 = nullptr;           // [cap][dim] tensor-core plane
+    float4* bound = nullptr;        // [cap] per-row error-bound entries (r, Dx, Dt, 0)
+    unsigned int* tile = nullptr;   // [seg_rows/256][4] per-tile maxima of the above (float bits)
+    int64_t cap = 0;                // rows allocated (multiple of 256, <= seg_rows)
+};
+
 struct drt_store {
     int dim = 0;          // row pitch in elements: the caller's dim rounded up to a multiple of 64, zero padded
     int dim_user = 0;     // the caller's embedding dim (rows / queries / reconstruct use this pitch)
+    int split = 0;        // dims [split, dim) are the caller-declared exactly-representable tail (default: none)
     int device = 0;
     int64_t seg_rows = 0;
     int64_t ntotal = 0;
     int sm_count = 148;
-    std::vector<float*> seg_f32;
-    std::vector<void*> seg_bf16;
+    std::vector<Segment> segs;
+    std::vector<float*> seg_f32;    // device pointer tables as the kernels take them (mirrors of segs)
+    std::vector<float4*> seg_bound;
+    double margin_scale = 1.0;      // widens k' after searches in which the certificate flagged many queries
     // search workspace (grow-only)
-    DevBuf q_bf16, q_f32, thr, cnt, cand, seg_table, out_scores, out_ids, misc;
+    DevBuf q_bf16, q_f32, thr, cnt, cand, seg_table, bound_table, qbound, out_scores, out_ids, misc;
     DevBuf qflag, sub_idx, sub_q, sub_os, sub_oi, sub_flag;   // exactness-check fallback
     int* err_host = nullptr;     // pinned + mapped: kernel watchdog code
     int* err_dev = nullptr;
@@ -165,9 +180,23 @@ namespace {
 // score tail the gap of m ranks at rank k is ~ m / k of the tail scale, so the margin grows
 // with k (mid-range k needs relatively more because the gap of few ranks fluctuates more).
 // Queries for which the a-posteriori check still fails are refined with a doubled k'.
-int kprime_for(int k) {
-    const int margin = k < 500 ? std::max(28, k / 5) : k / 8 + 38;
-    return (k + margin + 3) & ~3;
+//
+// With the rigorous certificate (mips_filter.cuh) the margin has to cover the worst-case error
+// bound E instead of the typical error (sqrt(dim) smaller): the gap between the exact k-th
+// score and the k'-th upper bound behaves like sigma_tail * ln(k'/k) with a spread of
+// sigma_tail * sqrt((k'-k) / (k k')) (top order statistics of a light tail), and must exceed E.
+// rho = E / sigma_tail is ~0.4 for 768-d Gaussian-like embeddings at N ~ 1e7 (E ~ 2.5 at score
+// scale 27.7: 2 |q| |d| 2^-8 / sqrt(6) + accumulation); k' is the smallest count with
+// ln(k'/k) >= rho + 4 sqrt((k'-k)/(k k')).  `scale` widens rho for stores whose searches flagged.
+int kprime_for(int k, double scale = 1.0) {
+    static const double rho0 = [] { const char* e = getenv("DRT_B200_KPRIME_RHO"); return e ? atof(e) : 0.40; }();
+    const double rho = rho0 * scale;
+    int kp = k + std::max(28, k / 5);
+    for (; kp < 8192; kp += 4) {
+        const double m = kp - k;
+        if (std::log((double)kp / k) >= rho + 4.0 * std::sqrt(m / ((double)k * kp))) break;
+    }
+    return std::min(8192, (kp + 3) & ~3);
 }
 
 // CTA-pair tiles (M=256) halve the corpus-operand smem/L2 traffic per FLOP and run ~10 % faster
@@ -186,8 +215,8 @@ int set_kernel_attrs(drt_store* s) {
                                   (int)drt::FilterCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(drt::mips_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)drt::FilterCfg<2>::kSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     s->attrs_set = true;
     return DRT_OK;
 }
@@ -212,6 +241,68 @@ int launch_filter(const CUtensorMap& tq, const CUtensorMap& td, const drt::Filte
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     CUDA_TRY(cudaLaunchKernelEx(&cfg, drt::mips_filter_kernel<kCtas>, tq, td, p));
+    return DRT_OK;
+}
+
+void free_segment(Segment& g) {
+    if (g.f32) cudaFree(g.f32);
+    if (g.bf16) cudaFree(g.bf16);
+    if (g.bound) cudaFree(g.bound);
+    if (g.tile) cudaFree(g.tile);
+    g = Segment();
+}
+
+int alloc_segment(const drt_store* s, Segment& g, int64_t cap) {
+    cudaError_t e = cudaMalloc((void**)&g.f32, (size_t)cap * s->dim * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&g.bf16, (size_t)cap * s->dim * 2);
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g.bound, (size_t)cap * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&g.tile, (size_t)(s->seg_rows / 256) * 16);
+    if (e != cudaSuccess) {
+        (void)cudaGetLastError();
+        free_segment(g);
+        return fail(DRT_E_OOM, "allocating a corpus segment of %lld rows x %d failed: %s", (long long)cap, s->dim,
+                    cudaGetErrorString(e));
+    }
+    g.cap = cap;
+    return DRT_OK;
+}
+
+// Make segment `seg` able to hold rows [0, need) (need <= seg_rows); rows [0, used) are live.
+// New segments are sized for what they must hold (at least 4096 rows, whole segments from a
+// quarter segment up); an under-sized last segment grows geometrically, moving its live rows.
+int ensure_segment(drt_store* s, int64_t seg, int64_t used, int64_t need, cudaStream_t st) {
+    auto round_cap = [&](int64_t rows) {
+        int64_t c = std::max<int64_t>(4096, (rows + 255) / 256 * 256);
+        if (4 * c >= s->seg_rows) c = s->seg_rows;
+        return std::min(c, s->seg_rows);
+    };
+    if ((size_t)seg == s->segs.size()) {
+        Segment g;
+        int rc = alloc_segment(s, g, round_cap(need));
+        if (rc != DRT_OK) return rc;
+        s->segs.push_back(g);
+        s->seg_f32.push_back(g.f32);
+        s->seg_bound.push_back(g.bound);
+    }
+    Segment& cur = s->segs[seg];
+    if (cur.cap < need) {
+        Segment g;
+        int rc = alloc_segment(s, g, round_cap(std::max(need, 2 * cur.cap)));
+        if (rc != DRT_OK) return rc;
+        if (used > 0) {
+            CUDA_TRY(cudaMemcpyAsync(g.f32, cur.f32, (size_t)used * s->dim * 4, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(g.bf16, cur.bf16, (size_t)used * s->dim * 2, cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(g.bound, cur.bound, (size_t)used * sizeof(float4), cudaMemcpyDeviceToDevice, st));
+            CUDA_TRY(cudaMemcpyAsync(g.tile, cur.tile, (size_t)(s->seg_rows / 256) * 16, cudaMemcpyDeviceToDevice, st));
+        }
+        CUDA_TRY(cudaStreamSynchronize(st));     // the old buffers may still be read by queued work
+        free_segment(cur);
+        cur = g;
+        s->seg_f32[seg] = g.f32;
+        s->seg_bound[seg] = g.bound;
+    }
+    // a segment that starts (again) at row 0 -- new, or reused after reset -- has no tile maxima yet
+    if (used == 0) CUDA_TRY(cudaMemsetAsync(cur.tile, 0, (size_t)(s->seg_rows / 256) * 16, st));
     return DRT_OK;
 }
 
@@ -270,10 +361,10 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                  int64_t id_offset, uint32_t flags, cudaStream_t st, int attempt, int kctas,
                  int keep_override, unsigned char* qflag, int64_t* flagged_out) {
     const int dim = s->dim;
-    const int keep = keep_override > 0 ? keep_override : kprime_for(k);
+    const int keep = keep_override > 0 ? keep_override : kprime_for(k, s->margin_scale);
     int cap = next_pow2(std::max(4 * keep, 4096));
     if (attempt >= 1) cap *= 4;
-    if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
+    if (cap > 16384) cap = 16384;        // select_kernel stages cap * 12 bytes in shared memory
     if (cap < 2 * keep) return fail(DRT_E_UNSUPPORTED, "k=%d too large for the candidate buffer", k);
 
     int rc;
@@ -283,6 +374,8 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     if ((rc = s->cand.ensure((size_t)nq * cap * 8)) != DRT_OK) return rc;
     if ((rc = s->misc.ensure(64)) != DRT_OK) return rc;
     if ((rc = s->seg_table.ensure(std::max<size_t>(8, s->seg_f32.size() * sizeof(float*)))) != DRT_OK) return rc;
+    if ((rc = s->bound_table.ensure(std::max<size_t>(8, s->seg_bound.size() * sizeof(float4*)))) != DRT_OK) return rc;
+    if ((rc = s->qbound.ensure((size_t)nq * sizeof(float4))) != DRT_OK) return rc;
 
     float* thr = (float*)s->thr.p;
     uint32_t* cnt = (uint32_t*)s->cnt.p;
@@ -293,14 +386,22 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     CUDA_TRY(cudaMemsetAsync(s->misc.p, 0, 64, st));
     CUDA_TRY(cudaMemcpyAsync(s->seg_table.p, s->seg_f32.data(), s->seg_f32.size() * sizeof(float*),
                              cudaMemcpyHostToDevice, st));
-    {
-        const size_t n4 = (size_t)nq * dim / 4;
-        const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)s->sm_count * 8);
-        drt::f32_to_bf16_kernel<<<blocks, 256, 0, st>>>((const float4*)q_dev, (uint2*)s->q_bf16.p, n4);
-        drt::init_query_state_kernel<<<(int)((nq + 255) / 256), 256, 0, st>>>(thr, cnt, (int)nq);
-        s->stats[0] += 2;
-    }
+    CUDA_TRY(cudaMemcpyAsync(s->bound_table.p, s->seg_bound.data(), s->seg_bound.size() * sizeof(float4*),
+                             cudaMemcpyHostToDevice, st));
     const bool exact_pass = (kctas == 0);    // fp32 SIMT first pass (last-resort refinement)
+    const float4* qbound = (const float4*)s->qbound.p;
+    const float4* const* bound_table = (const float4* const*)s->bound_table.p;
+    {
+        // error-model constants of the certificate (mips_filter.cuh): the tensor core accumulates
+        // dim/16 K=16 steps, each at worst 18 truncations of 2^-23 relative to the running
+        // magnitude; the rescoring dot (K2) rounds dim/128 FMAs + 7 adds per lane chain.
+        const float c_acc = (float)(dim / 16) * 18.f * 0x1p-23f;
+        const float c_k2 = (float)(dim / 128 + 8) * 0x1p-23f;
+        const int blocks = (int)std::min<int64_t>((nq + 7) / 8, (int64_t)s->sm_count * 8);
+        drt::prep_queries_kernel<<<blocks, 256, 0, st>>>(q_dev, (int)nq, dim, s->split, exact_pass ? nullptr : (uint2*)s->q_bf16.p,
+                                                        (float4*)s->qbound.p, thr, cnt, c_acc, c_k2, exact_pass ? 1 : 0);
+        s->stats[0] += 1;
+    }
     CUtensorMap tmap_q;
     if (!exact_pass && (rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
 
@@ -319,13 +420,14 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
             dim3 grid((unsigned)((nrows + C::BN - 1) / C::BN), (unsigned)((nq + C::BM - 1) / C::BM));
             drt::exact_filter_kernel<C><<<grid, C::THREADS, 0, st>>>(
                 q_dev, (long long)nq, rows, (long long)nrows, dim, (uint32_t)((int64_t)c.seg * s->seg_rows + c.row0), thr,
-                cnt, cand, (uint32_t)cap, aligned16_ptr(q_dev) ? 1 : 0);
-            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
+                cnt, cand, (uint32_t)cap, aligned16_ptr(q_dev) ? 1 : 0, qbound, s->seg_bound[c.seg] + c.row0);
+            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 12, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow,
+                                                                      qbound, bound_table, (uint32_t)s->seg_rows);
             s->stats[0] += 2;
             continue;
         }
         if (c.seg != tmap_seg) {
-            if ((rc = make_tmap_bf16(&tmap_d, s->seg_bf16[c.seg], (uint64_t)seg_valid, (uint64_t)dim,
+            if ((rc = make_tmap_bf16(&tmap_d, s->segs[c.seg].bf16, (uint64_t)seg_valid, (uint64_t)dim,
                                      drt::kTileN / kctas)) != DRT_OK) return rc;
             tmap_seg = c.seg;
         }
@@ -346,6 +448,8 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         p.row_base = (uint32_t)((int64_t)c.seg * s->seg_rows);
         p.cap = (uint32_t)cap;
         p.thr = thr; p.cnt = cnt; p.cand = cand; p.err = s->err_dev;
+        p.qbound = qbound;
+        p.tile_bound = (const float4*)s->segs[c.seg].tile;
         const bool timed = (flags & DRT_SEARCH_TIME_KERNELS) != 0;
         if (timed) {
             while (s->ev.size() < 2 * (n_timed + 1)) {
@@ -366,7 +470,8 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         const int64_t seen = (int64_t)c.seg * s->seg_rows + c.row1;
         const bool last = (&c == &chunks.back());
         if (!frozen || last) {
-            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 8, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow);
+            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 12, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow,
+                                                                      qbound, bound_table, (uint32_t)s->seg_rows);
             s->stats[0] += 1;
             if (attempt == 0 && (double)keep * (double)(s->ntotal - seen) / (double)seen < (double)(cap - keep) / 8.0) frozen = true;
         }
@@ -379,7 +484,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                                                        (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
                                                        (long long)id_offset, out_s, (long long*)out_i,
                                                        (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag,
-                                                       exact_pass ? 0 : 1);
+                                                       exact_pass ? 0 : 1, thr);
         s->stats[0] += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -418,10 +523,10 @@ int search_retrying(drt_store* s, const float* q_dev, int64_t nq, int k, float* 
 // (up to 3 rounds); what is still flagged afterwards is reported in stats[4].
 int refine_flagged(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
                    int64_t id_offset, uint32_t flags, cudaStream_t st, unsigned char* qflag, int64_t* flagged) {
-    int keep = kprime_for(k);
+    int keep = kprime_for(k, s->margin_scale);
     std::vector<unsigned char> hflag;
     std::vector<int> idx;
-    for (int round = 0; *flagged > 0 && round < 3 && keep * 2 <= 4096; ++round) {
+    for (int round = 0; *flagged > 0 && round < 3 && keep * 2 <= 8192; ++round) {
         keep *= 2;
         hflag.resize((size_t)nq);
         CUDA_TRY(cudaMemcpyAsync(hflag.data(), qflag, (size_t)nq, cudaMemcpyDeviceToHost, st));
@@ -522,7 +627,7 @@ int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows) {
     if (!g.ok) return fail(DRT_E_CUDA, "cudaSetDevice(%d) failed", device);
     drt_store* s = new (std::nothrow) drt_store();
     if (!s) return fail(DRT_E_OOM, "host allocation failed");
-    s->dim = dim_pad; s->dim_user = dim; s->device = device; s->seg_rows = seg_rows;
+    s->dim = dim_pad; s->dim_user = dim; s->split = dim_pad; s->device = device; s->seg_rows = seg_rows;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaHostAlloc((void**)&s->err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&s->err_dev, s->err_host, 0) != cudaSuccess ||
@@ -540,8 +645,7 @@ int drt_store_destroy(drt_store* s) {
     if (!s) return DRT_OK;
     DeviceGuard g(s->device);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
-    for (float* p : s->seg_f32) cudaFree(p);
-    for (void* p : s->seg_bf16) cudaFree(p);
+    for (Segment& g : s->segs) free_segment(g);
     s->q_bf16.release(); s->q_f32.release(); s->thr.release(); s->cnt.release(); s->cand.release();
     s->seg_table.release(); s->out_scores.release(); s->out_ids.release(); s->misc.release();
     s->qflag.release(); s->sub_idx.release(); s->sub_q.release(); s->sub_os.release(); s->sub_oi.release(); s->sub_flag.release();
@@ -564,39 +668,37 @@ int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device
     int64_t done = 0;
     while (done < n) {
         const int64_t seg = s->ntotal / s->seg_rows, off = s->ntotal % s->seg_rows;
-        if ((size_t)seg == s->seg_f32.size()) {
-            float* f = nullptr; void* b = nullptr;
-            cudaError_t e = cudaMalloc((void**)&f, (size_t)s->seg_rows * row_f32);
-            if (e == cudaSuccess) e = cudaMalloc(&b, (size_t)s->seg_rows * row_bf16);
-            if (e != cudaSuccess) {
-                (void)cudaGetLastError();
-                if (f) cudaFree(f);
-                return fail(DRT_E_OOM, "allocating corpus segment %lld (%lld rows x %d) failed: %s", (long long)seg,
-                            (long long)s->seg_rows, s->dim, cudaGetErrorString(e));
-            }
-            if (s->dim_user != s->dim) {   // padding columns stay zero for the life of the segment
-                e = cudaMemsetAsync(f, 0, (size_t)s->seg_rows * row_f32, st);
-                if (e != cudaSuccess) { (void)cudaGetLastError(); cudaFree(f); cudaFree(b); return fail(DRT_E_CUDA, "cudaMemsetAsync failed: %s", cudaGetErrorString(e)); }
-            }
-            s->seg_f32.push_back(f); s->seg_bf16.push_back(b);
-        }
         const int64_t take = std::min(n - done, s->seg_rows - off);
-        float* dst = s->seg_f32[seg] + (size_t)off * s->dim;
+        int rc = ensure_segment(s, seg, off, off + take, st);
+        if (rc != DRT_OK) return rc;
+        Segment& sg = s->segs[seg];
+        float* dst = sg.f32 + (size_t)off * s->dim;
         const cudaMemcpyKind kind = rows_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
-        if (s->dim_user == s->dim)
+        if (s->dim_user == s->dim) {
             CUDA_TRY(cudaMemcpyAsync(dst, rows + (size_t)done * s->dim, (size_t)take * row_f32, kind, st));
-        else
+        } else {   // rows are stored zero-padded to the pitch
+            CUDA_TRY(cudaMemsetAsync(dst, 0, (size_t)take * row_f32, st));
             CUDA_TRY(cudaMemcpy2DAsync(dst, row_f32, rows + (size_t)done * s->dim_user, (size_t)s->dim_user * 4,
                                        (size_t)s->dim_user * 4, (size_t)take, kind, st));
-        const size_t n4 = (size_t)take * s->dim / 4;
-        const int blocks = (int)std::min<size_t>((n4 + 255) / 256, (size_t)s->sm_count * 16);
-        drt::f32_to_bf16_kernel<<<blocks, 256, 0, st>>>((const float4*)dst,
-            (uint2*)((char*)s->seg_bf16[seg] + (size_t)off * row_bf16), n4);
+        }
+        const int blocks = (int)std::min<int64_t>((take + 7) / 8, (int64_t)s->sm_count * 16);
+        drt::ingest_rows_kernel<<<blocks, 256, 0, st>>>(dst, (long long)take, s->dim, s->split,
+                                                       (uint2*)((char*)sg.bf16 + (size_t)off * row_bf16), sg.bound, sg.tile,
+                                                       (long long)off);
         CUDA_TRY(cudaGetLastError());
         s->ntotal += take;
         done += take;
     }
     if (!rows_on_device) CUDA_TRY(cudaStreamSynchronize(st));
+    return DRT_OK;
+}
+
+int drt_store_set_exact_tail(drt_store* s, int tail_dims) {
+    if (!s) return fail(DRT_E_INVALID, "store is NULL");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (tail_dims < 0 || tail_dims > s->dim_user) return fail(DRT_E_INVALID, "tail_dims %d out of range [0,%d]", tail_dims, s->dim_user);
+    if (s->ntotal != 0) return fail(DRT_E_INVALID, "the exact tail must be declared before the first add");
+    s->split = tail_dims == 0 ? s->dim : s->dim_user - tail_dims;
     return DRT_OK;
 }
 
@@ -693,6 +795,10 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
             int64_t flagged = 0;
             rc = search_retrying(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, kctas, 0,
                                  (unsigned char*)s->qflag.p, &flagged);
+            s->stats[9] += flagged;
+            // a store whose searches keep flagging (its score gaps are small against the error
+            // bound) gets a wider first-pass margin from now on instead of paying the ladder
+            if (flagged > std::max<int64_t>(1, nb / 50) && s->margin_scale < 8.0) s->margin_scale *= 1.5;
             if (rc == DRT_OK && flagged > 0 && !(flags & DRT_SEARCH_NO_RESCORE)) {
                 rc = refine_flagged(s, q_dev, nb, k, os_dev, oi_dev, id_offset, flags, st, (unsigned char*)s->qflag.p, &flagged);
                 if (rc == DRT_OK && flagged > 0)
@@ -716,7 +822,7 @@ int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_
     const int keep = kprime_for(k);
     int cap = next_pow2(std::max(4 * keep, 4096));
     if (attempt >= 1) cap *= 4;
-    if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
+    if (cap > 16384) cap = 16384;
     const std::vector<Chunk> chunks = plan_chunks(ntotal, seg_rows, cap, keep, attempt);
     for (size_t i = 0; i < chunks.size() && (int)i < max_chunks && out; ++i) {
         out[3 * i] = chunks[i].seg; out[3 * i + 1] = chunks[i].row0; out[3 * i + 2] = chunks[i].row1;
@@ -729,7 +835,7 @@ int drt_plan_params(int k, int attempt, int* kprime, int* cap_out) {
     const int keep = kprime_for(k);
     int cap = next_pow2(std::max(4 * keep, 4096));
     if (attempt >= 1) cap *= 4;
-    if ((size_t)cap * 8 > 160 * 1024) cap = 16384;
+    if (cap > 16384) cap = 16384;
     if (kprime) *kprime = keep;
     if (cap_out) *cap_out = cap;
     return DRT_OK;

@@ -52,7 +52,9 @@ struct FilterParams {
     uint32_t rows_valid;    // rows of this segment that may be admitted by this launch
     uint32_t row_base;      // store row id of the segment's first row
     uint32_t cap;           // candidate slots per query
-    const float* thr;       // [nq] admission threshold (strict >)
+    const float* thr;       // [nq] admission threshold on the UPPER-BOUND score (strict >)
+    const float4* qbound;   // [nq] per-query error-bound coefficients (A, B, C, -), see below
+    const float4* tile_bound; // this segment's per-256-row-tile maxima of the row bounds (r, Dx, Dt, -)
     uint32_t* cnt;          // [nq] candidates appended so far (may exceed cap: overflow)
     uint64_t* cand;         // [nq][cap] packed (ordered score << 32 | ~row)
     int* err;               // host-mapped watchdog flag
@@ -70,6 +72,24 @@ __device__ __forceinline__ float ordered_to_float(uint32_t o) {
 }
 __device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
     return (static_cast<uint64_t>(float_to_ordered(score)) << 32) | (0xFFFFFFFFu - row);
+}
+
+// ---- exactness certificate: a rigorous bound on |first-pass score - fp32 rescoring score| -----
+// Row j stores rb = (r, Dx, Dt): r = |d - bf16(d)|_2 over all dims, Dx = |d[0:split)|_2,
+// Dt = |d[split:)|_2 (split = dim unless the caller declares an exactly-representable tail);
+// query q carries qb = (A, B, C) = (|q~|(1+c_acc), e_x + c, e_t + c) with q~ = bf16(q),
+// e_x / e_t = |q - q~|_2 over the head / tail dims and c = c_acc |q~| + c_32 |q| covering the
+// tensor core's fp32 accumulation (worst case: operands aligned to the largest exponent and
+// TRUNCATED, 18 ulp of the running magnitude per K=16 step) and the rounding of the fp32
+// rescoring dot.  By Cauchy-Schwarz, term by term,
+//     s_fp32(q,j)  <=  ub(q,j) := s~(q,j) + A r + B Dx + C Dt            (all roundings upward)
+// The first pass keeps, per query, the k' rows with the largest ub; every other row has
+// ub <= thr (the k'-th largest ub), so once the exact k-th score exceeds thr no other row can
+// belong to the top-k: a proof, not an estimate.  K1 tests against the 256-row tile maxima
+// (ub_tile >= ub_row: a superset is admitted), select_kernel re-evaluates ub per row.
+constexpr float kBoundHuge = 1e30f;     // stands in for non-finite norms (keeps 0 * x finite)
+__device__ __forceinline__ float bound_term(const float4& qb, const float4& rb) {
+    return __fmaf_ru(qb.x, rb.x, __fmaf_ru(qb.y, rb.y, __fmul_ru(qb.z, rb.z)));
 }
 
 template <int kCtas>
@@ -295,13 +315,18 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
             const int q = (m_tile * kCtas + static_cast<int>(rank)) * kTileM + quarter * 32 + lane;
             const float thr = (q < p.nq) ? p.thr[q] : __int_as_float(0x7f800000);
             const int qc = (q < p.nq) ? q : 0;
+            const float4 qb = __ldg(p.qbound + qc);
             for (int nt = nt0; nt < nt1; ++nt, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1u;
                 const uint32_t row0 = static_cast<uint32_t>(p.n_tile_begin + nt) * kTileN;
                 const int valid_cols = static_cast<int>(min(p.rows_valid - row0, static_cast<uint32_t>(kTileN)));
+                // the tile's error bound (warp-uniform 16-byte load, in flight while the MMA finishes):
+                // a row is admitted when its UPPER-BOUND score s~ + E can exceed the threshold
+                const float4 tb = __ldg(p.tile_bound + p.n_tile_begin + nt);
                 ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err, 104);
                 ptx::tc_fence_after();
+                const float thr_eff = __fsub_rd(thr, bound_term(qb, tb));
 
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN + half * kColsPerWarp;
                 const uint32_t col0 = half * kColsPerWarp;
@@ -311,10 +336,10 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 for (int c = 0; c < kColsPerWarp / 32; c += 2) {
                     tmem_ld_wait_regs(va);
                     ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-                    filter_chunk(va, thr, p.row_base + row0 + col0 + c * 32, valid_cols - static_cast<int>(col0) - c * 32, my_stage, scnt, p, qc);
+                    filter_chunk(va, thr_eff, p.row_base + row0 + col0 + c * 32, valid_cols - static_cast<int>(col0) - c * 32, my_stage, scnt, p, qc);
                     tmem_ld_wait_regs(vb);
                     if (c + 2 < kColsPerWarp / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                    filter_chunk(vb, thr, p.row_base + row0 + col0 + (c + 1) * 32, valid_cols - static_cast<int>(col0) - (c + 1) * 32, my_stage, scnt, p, qc);
+                    filter_chunk(vb, thr_eff, p.row_base + row0 + col0 + (c + 1) * 32, valid_cols - static_cast<int>(col0) - (c + 1) * 32, my_stage, scnt, p, qc);
                 }
                 // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
                 ptx::tc_fence_before();

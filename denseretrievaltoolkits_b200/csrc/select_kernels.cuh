@@ -35,15 +35,80 @@ __device__ __forceinline__ void bitonic_sort_desc_u64(uint64_t* keys, int P) {
     __syncthreads();
 }
 
-__global__ void init_query_state_kernel(float* thr, uint32_t* cnt, int nq) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < nq) { thr[i] = -FLT_MAX; cnt[i] = 0u; }   // faiss: heap starts at -FLT_MAX
+// Query preparation, one warp per query: fp32 -> bf16 (round to nearest even) for the tensor-core
+// pass, the query's error-bound coefficients qb = (A, B, C) (mips_filter.cuh), and the initial
+// search state (threshold -FLT_MAX like faiss' heap, empty candidate list).
+//   exact_mode = 1 (fp32 SIMT first pass of the last-resort refinement): A = B = C = 0, rows are
+//   selected by their fp32 scores as they are (exact ties keep the canonical id order).
+__global__ void __launch_bounds__(256)
+prep_queries_kernel(const float* __restrict__ q, int nq, int dim, int split, uint2* __restrict__ q_bf16,
+                    float4* __restrict__ qbound, float* __restrict__ thr, uint32_t* __restrict__ cnt,
+                    float c_acc, float c_32, int exact_mode) {
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const float up = 1.f + 0x1p-10f;      // covers the rounding of the fp32 sums / sqrt below
+    for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
+        const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(i) * dim);
+        uint2* dst = q_bf16 ? q_bf16 + static_cast<size_t>(i) * (dim >> 2) : nullptr;
+        float s_t = 0.f, s_ex = 0.f, s_et = 0.f, s_n = 0.f;
+        for (int j = lane; j < (dim >> 2); j += 32) {
+            const float4 v = src[j];
+            const float x[4] = {v.x, v.y, v.z, v.w};
+            float xt[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                xt[c] = __bfloat162float(__float2bfloat16_rn(x[c]));
+                const float e = x[c] - xt[c];                  // exact in fp32
+                s_t = fmaf(xt[c], xt[c], s_t);
+                s_n = fmaf(x[c], x[c], s_n);
+                if (4 * j + c < split) s_ex = fmaf(e, e, s_ex); else s_et = fmaf(e, e, s_et);
+            }
+            if (dst) {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+                uint2 o;
+                o.x = *reinterpret_cast<const uint32_t*>(&lo);
+                o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                dst[j] = o;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s_t += __shfl_xor_sync(0xffffffffu, s_t, o);
+            s_n += __shfl_xor_sync(0xffffffffu, s_n, o);
+            s_ex += __shfl_xor_sync(0xffffffffu, s_ex, o);
+            s_et += __shfl_xor_sync(0xffffffffu, s_et, o);
+        }
+        if (lane == 0) {
+            const float nt = sqrtf(s_t) * up, nn = sqrtf(s_n) * up;
+            float A, B, C;
+            if (exact_mode) {
+                A = B = C = 0.f;
+            } else {
+                const float c = (c_acc * nt + c_32 * nn) * up;
+                A = nt * (1.f + c_acc) * up;
+                B = (sqrtf(s_ex) * up + c) * up;
+                C = (sqrtf(s_et) * up + c) * up;
+            }
+            if (!(A < kBoundHuge)) A = kBoundHuge;             // also catches NaN
+            if (!(B < kBoundHuge)) B = kBoundHuge;
+            if (!(C < kBoundHuge)) C = kBoundHuge;
+            qbound[i] = make_float4(A, B, C, 0.f);
+            thr[i] = -FLT_MAX;                                  // faiss: heap starts at -FLT_MAX
+            cnt[i] = 0u;
+        }
+    }
 }
 
 // K-select: one CTA per query.  If the query gathered more than `keep` candidates, keep the
-// best `keep` (score desc, row asc) and publish the keep-th score as the new admission
-// threshold.  Chunks are visited in ascending row order and admission is strict (>), so a later
-// row that ties the threshold loses to the earlier one — the same outcome as faiss' heap.
+// `keep` with the largest UPPER-BOUND score ub = s~ + E(q,row) (ties: row asc) and publish the
+// keep-th ub as the new admission threshold.  Every row that was never admitted, or is dropped
+// here, has ub <= that threshold, hence an exact score <= it: the invariant K2's exactness
+// certificate rests on.  Chunks are visited in ascending row order and admission is strict (>).
+//
+// The candidate lists hold RAW first-pass scores; the per-row bound is gathered here (16 B per
+// candidate from the store's row-bound table), ub keys are formed in shared memory, and the
+// survivors are written back with their raw scores again.
 //
 // Selection is an MSD radix select on the packed 64-bit keys (8 bits per pass, 256-bin smem
 // histogram, warp-parallel suffix scan to locate the bin holding the keep-th largest key), O(n)
@@ -52,8 +117,10 @@ __global__ void init_query_state_kernel(float* thr, uint32_t* cnt, int nq) {
 // neither the filter kernel nor later selects need order, and K2 sorts its own output.
 __global__ void __launch_bounds__(256)
 select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t keep,
-              int* overflow) {
-    extern __shared__ uint64_t s_keys[];
+              int* overflow, const float4* __restrict__ qbound, const float4* const* __restrict__ seg_bound,
+              uint32_t seg_rows) {
+    extern __shared__ uint64_t s_keys[];             // [cap] ub keys, then [cap] raw ordered scores
+    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_keys + cap);
     __shared__ uint32_t s_hist[256];
     __shared__ uint32_t s_bin, s_need, s_bucket, s_out;
     __shared__ uint64_t s_pivot;
@@ -66,7 +133,17 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
     }
     if (n <= keep) return;
     uint64_t* row = cand + static_cast<size_t>(q) * cap;
-    for (uint32_t i = tid; i < n; i += blockDim.x) s_keys[i] = row[i];
+    const float4 qb = qbound[q];
+    for (uint32_t i = tid; i < n; i += blockDim.x) {
+        const uint64_t key = row[i];
+        const uint32_t lo = static_cast<uint32_t>(key), raw = static_cast<uint32_t>(key >> 32);
+        const uint32_t r = 0xFFFFFFFFu - lo;
+        const uint32_t seg = r / seg_rows;
+        const float4 rb = __ldg(seg_bound[seg] + (r - seg * seg_rows));
+        const float ub = __fadd_ru(ordered_to_float(raw), bound_term(qb, rb));
+        s_raw[i] = raw;
+        s_keys[i] = (static_cast<uint64_t>(float_to_ordered(ub)) << 32) | lo;
+    }
     if (tid == 0) { s_need = keep; s_out = 0; }
     uint64_t prefix = 0, mask = 0;
     bool found = false;
@@ -116,7 +193,7 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
     const uint64_t pivot = found ? s_pivot : prefix;
     for (uint32_t i = tid; i < n; i += blockDim.x) {
         const uint64_t key = s_keys[i];
-        if (key >= pivot) row[atomicAdd(&s_out, 1u)] = key;
+        if (key >= pivot) row[atomicAdd(&s_out, 1u)] = (static_cast<uint64_t>(s_raw[i]) << 32) | (key & 0xFFFFFFFFull);
     }
     if (tid == 0) {
         cnt[q] = keep;
@@ -131,15 +208,13 @@ __global__ void __launch_bounds__(256)
 rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t keep,
                const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
                int k, long long id_offset, float* out_scores, long long* out_ids,
-               int do_rescore, unsigned long long* flagged, unsigned char* qflag, int check) {
+               int do_rescore, unsigned long long* flagged, unsigned char* qflag, int check,
+               const float* __restrict__ thr) {
     extern __shared__ uint64_t s_keys[];            // [P] then dim floats
     const int q = blockIdx.x;
     const int n = static_cast<int>(min(min(cnt[q], cap), keep));
     const int P = next_pow2_dev(max(n, 1));
     float* s_q = reinterpret_cast<float*>(s_keys + next_pow2_dev(static_cast<int>(keep)));
-    __shared__ unsigned int s_emax;   // max |approx - exact| (bits of a non-negative float)
-    __shared__ unsigned int s_amin;   // min approx score (ordered encoding)
-    if (threadIdx.x == 0) { s_emax = 0u; s_amin = 0xFFFFFFFFu; }
     for (int j = threadIdx.x; j < dim; j += blockDim.x) s_q[j] = q_f32[static_cast<size_t>(q) * dim + j];
     __syncthreads();
 
@@ -163,12 +238,8 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
             if (lane == 0) {
-                const uint32_t approx_o = static_cast<uint32_t>(key >> 32);
-                const float approx = ordered_to_float(approx_o);
                 const bool ok = acc > -FLT_MAX;    // also false for NaN
                 s_keys[i] = ok ? pack_key(acc, r) : 0ull;
-                atomicMin(&s_amin, approx_o);
-                if (ok) atomicMax(&s_emax, __float_as_uint(fabsf(acc - approx)));
             }
         }
     } else {
@@ -188,16 +259,19 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
             out_ids[o] = -1;
         }
     }
-    // Exactness check: rows that never became candidates have bf16 score <= a_min.  If the
-    // candidate list was full and a_min plus twice the largest observed bf16 error reaches the
-    // exact k-th score, a non-candidate could belong to the top-k: count the query as flagged.
+    // Exactness certificate.  Every row that is not in this list has an upper-bound score
+    // ub <= thr[q] (select_kernel's invariant; thr is still -FLT_MAX when nothing was ever
+    // dropped), and ub bounds the value THIS kernel would compute for that row.  So if the exact
+    // k-th score lies strictly above thr[q], no other row can belong to the top-k: proven exact.
+    // Otherwise the query is flagged and the host searches it again (larger k', then fp32).
     if (threadIdx.x == 0) {
         bool flag = false;
-        if (check && do_rescore && n == static_cast<int>(keep) && n >= k && s_keys[k - 1] != 0ull) {
-            const float tau = ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32));
-            const float amin = ordered_to_float(s_amin);
-            const float emax = __uint_as_float(s_emax);
-            flag = amin + 2.f * emax >= tau;
+        if (check && do_rescore) {
+            const float bound = thr[q];
+            if (bound > -FLT_MAX) {
+                const bool have_k = n >= k && s_keys[k - 1] != 0ull;
+                flag = !have_k || !(ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32)) > bound);
+            }
         }
         if (flag) atomicAdd(flagged, 1ull);
         if (qflag) qflag[q] = flag ? 1 : 0;
@@ -232,7 +306,7 @@ template <class Cfg>
 __global__ void __launch_bounds__(Cfg::THREADS)
 exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __restrict__ rows, long long nrows,
                     int dim, uint32_t row_id0, const float* __restrict__ thr, uint32_t* cnt, uint64_t* cand,
-                    uint32_t cap, int vec_ok) {
+                    uint32_t cap, int vec_ok, const float4* __restrict__ qbound, const float4* __restrict__ row_bound) {
     constexpr int TM = Cfg::TM, TN = Cfg::TN;
     const long long m0 = static_cast<long long>(blockIdx.y) * Cfg::BM;
     const long long n0 = static_cast<long long>(blockIdx.x) * Cfg::BN;
@@ -244,10 +318,12 @@ exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __re
         const long long qi = m0 + Cfg::row_of(ty, i);
         if (qi >= nq) continue;
         const float t = thr[qi];
+        const float4 qb = qbound[qi];
 #pragma unroll
         for (int j = 0; j < TN; ++j) {
             const long long col = n0 + Cfg::col_of(tx, j);
-            if (col < nrows && acc[i][j] > t) {
+            // same rule as K1: admit when the upper bound (here only fp32 summation-order slack) beats thr
+            if (col < nrows && acc[i][j] > __fsub_rd(t, bound_term(qb, __ldg(row_bound + col)))) {
                 const uint32_t slot = atomicAdd(cnt + qi, 1u);
                 if (slot < cap) cand[static_cast<size_t>(qi) * cap + slot] = pack_key(acc[i][j], row_id0 + static_cast<uint32_t>(col));
             }
@@ -255,7 +331,58 @@ exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __re
     }
 }
 
-// K6 ingest: fp32 rows -> bf16 plane (round to nearest even), 16 B in / 8 B out per thread step
+// K6 ingest, one warp per row: fp32 row -> bf16 plane (round to nearest even) plus the row's entry
+// of the error-bound table rb = (|d - bf16(d)|, |d[0:split)|, |d[split:)|, 0), each rounded up,
+// and the component-wise maxima of the row's 256-row tile (atomicMax on the bit patterns of
+// non-negative floats).  Non-finite norms are stored as kBoundHuge.  HBM-bound: 4 B in, 2 B out
+// per element, 16 B per row.
+__global__ void __launch_bounds__(256)
+ingest_rows_kernel(const float* __restrict__ plane, long long n, int dim, int split, uint2* __restrict__ bf16,
+                   float4* __restrict__ row_bound, unsigned int* __restrict__ tile_bound, long long row0) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+    const float up = 1.f + 0x1p-10f;
+    for (long long i = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; i < n; i += warps) {
+        const float4* src = reinterpret_cast<const float4*>(plane + static_cast<size_t>(i) * dim);
+        uint2* dst = bf16 + static_cast<size_t>(i) * (dim >> 2);
+        float s_r = 0.f, s_x = 0.f, s_t = 0.f;
+        for (int j = lane; j < (dim >> 2); j += 32) {
+            const float4 v = src[j];
+            const float x[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const float e = x[c] - __bfloat162float(__float2bfloat16_rn(x[c]));   // exact in fp32
+                s_r = fmaf(e, e, s_r);
+                if (4 * j + c < split) s_x = fmaf(x[c], x[c], s_x); else s_t = fmaf(x[c], x[c], s_t);
+            }
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 o;
+            o.x = *reinterpret_cast<const uint32_t*>(&lo);
+            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            dst[j] = o;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s_r += __shfl_xor_sync(0xffffffffu, s_r, o);
+            s_x += __shfl_xor_sync(0xffffffffu, s_x, o);
+            s_t += __shfl_xor_sync(0xffffffffu, s_t, o);
+        }
+        if (lane == 0) {
+            float r = sqrtf(s_r) * up, dx = sqrtf(s_x) * up, dt = sqrtf(s_t) * up;
+            if (!(r < kBoundHuge)) r = kBoundHuge;
+            if (!(dx < kBoundHuge)) dx = kBoundHuge;
+            if (!(dt < kBoundHuge)) dt = kBoundHuge;
+            row_bound[row0 + i] = make_float4(r, dx, dt, 0.f);
+            unsigned int* tb = tile_bound + 4 * ((row0 + i) >> 8);
+            atomicMax(tb + 0, __float_as_uint(r));
+            atomicMax(tb + 1, __float_as_uint(dx));
+            atomicMax(tb + 2, __float_as_uint(dt));
+        }
+    }
+}
+
+// fp32 -> bf16 plane conversion only (16 B in / 8 B out per thread step)
 __global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restrict__ out, size_t n4) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n4;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {

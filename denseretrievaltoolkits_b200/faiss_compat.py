@@ -143,7 +143,7 @@ class IndexFlatIP:
         buf = (ctypes.c_int64 * 12)()
         _lib.check(self._lib.drt_search_stats(self._h, buf), "search_stats")
         names = ["launches", "filter_launches", "overflow_retries", "kprime", "flagged_queries",
-                 "ctas_per_tile", "chunks", "filter_ns", "exact_queries"]
+                 "ctas_per_tile", "chunks", "filter_ns", "exact_queries", "refined_queries"]
         return dict(zip(names, [int(v) for v in buf]))
 
     # ---- reconstruct ------------------------------------------------------------------------
@@ -197,6 +197,9 @@ class IndexFlatL2:
         self.is_trained = True
         self.verbose = False
         self._ip = IndexFlatIP(self.d + 3, device=device, seg_rows=seg_rows)
+        # the three norm columns (and the query's ones) are exact in bf16: let the exactness
+        # certificate bound the rounding error of the head dims only
+        _lib.check(self._ip._lib.drt_store_set_exact_tail(self._ip._h, 3), "set_exact_tail")
 
     @property
     def ntotal(self) -> int:

@@ -20,7 +20,7 @@
 extern "C" {
 #endif
 
-#define DRT_B200_ABI_VERSION 1
+#define DRT_B200_ABI_VERSION 2
 
 /* status codes */
 #define DRT_OK                0
@@ -71,6 +71,15 @@ int drt_store_destroy(drt_store* s);
  * Stream-ordered on `stream`; with a host source the call returns after the copy completed. */
 int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device, void* stream);
 
+/* Declares that the LAST `tail_dims` dims of every row and query are exactly representable in
+ * bf16 (e.g. the norm-augmentation columns of the squared-L2 form of faiss.index_factory(d,
+ * "Flat"), index.py:50): the exactness certificate then bounds the rounding error of the head
+ * and tail dims separately, which keeps it tight when the tail carries most of a row's norm.
+ * Purely an accuracy hint for the bound — results are exact either way (rows whose tail is not
+ * exact are still covered: the residual norm is always taken over all dims).  Call before the
+ * first add. */
+int drt_store_set_exact_tail(drt_store* s, int tail_dims);
+
 int64_t drt_store_ntotal(const drt_store* s);   /* index.ntotal */
 int     drt_store_dim(const drt_store* s);      /* index.d      */
 int     drt_store_device(const drt_store* s);
@@ -99,7 +108,9 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k,
  *  [3] first-pass candidates per query (k')      [4] queries whose exactness check flagged
  *  [5] ctas per tile (1|2)                        [6] corpus chunks
  *  [7] summed device time of the MMA-filter launches in ns (DRT_SEARCH_TIME_KERNELS only)
- *  [8] queries that needed the exact fp32 first pass (last-resort refinement)  [9..11] reserved */
+ *  [8] queries that needed the exact fp32 first pass (last-resort refinement)
+ *  [9] queries whose certificate failed after the FIRST pass (searched again with a larger k';
+ *      [4] counts what is still uncertified after the whole ladder)           [10..11] reserved */
 int drt_search_stats(const drt_store* s, int64_t out[12]);
 
 /* Host-side planning, exposed for tests (no device needed).  drt_plan_params: k' (first-pass

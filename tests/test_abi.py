@@ -26,7 +26,7 @@ def test_header_and_binding_list_agree():
 def test_library_exports_every_declared_symbol(built_lib):
     for name in _header_symbols():
         assert hasattr(built_lib, name), name
-    assert built_lib.drt_abi_version() == 1
+    assert built_lib.drt_abi_version() == 2
 
 
 def test_build_command_targets_sm100a():
