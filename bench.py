@@ -133,6 +133,44 @@ def fill_rows(torch, add_fn, row0: int, row1: int, device):
         c += 1
 
 
+def parity_check(torch, dist, world, rank, device, row0, row1, q_dev, k, D, I, nsub=128):
+    """Result check OUTSIDE the timed region, at every N: a fixed subset of the queries against an
+    independent exact search — fp32 torch.matmul (TF32 off) + topk over this rank's rows,
+    regenerated from the chunk seeds (not read back from the store), the per-rank top-k lists
+    all-gathered and merged with torch.topk.  The global top-k must equal the single-index top-k
+    (reference semantic: DRT/model/utils.py:215-229)."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sel = torch.linspace(0, q_dev.shape[0] - 1, min(nsub, q_dev.shape[0]), device=device).long()
+    qs = q_dev.index_select(0, sel)
+    bd = torch.full((qs.shape[0], k), float("-inf"), device=device)
+    bi = torch.full((qs.shape[0], k), -1, dtype=torch.int64, device=device)
+    c = row0 // CHUNK
+    while c * CHUNK < row1:
+        lo, hi = max(row0, c * CHUNK), min(row1, (c + 1) * CHUNK)
+        rows = make_corpus_chunk(torch, c, device)[lo - c * CHUNK: hi - c * CHUNK]
+        kk = min(k, rows.shape[0])
+        d, i = torch.topk(qs @ rows.t(), kk, dim=1)
+        md, mi = torch.cat([bd, d], 1), torch.cat([bi, i + lo], 1)
+        bd, o = torch.topk(md, k, dim=1)
+        bi = torch.gather(mi, 1, o)
+        del rows
+        c += 1
+    if world > 1:
+        gd = torch.empty((world,) + tuple(bd.shape), device=device)
+        gi = torch.empty((world,) + tuple(bi.shape), dtype=torch.int64, device=device)
+        dist.all_gather_into_tensor(gd, bd.contiguous())
+        dist.all_gather_into_tensor(gi, bi.contiguous())
+        md, mi = gd.permute(1, 0, 2).reshape(qs.shape[0], -1), gi.permute(1, 0, 2).reshape(qs.shape[0], -1)
+        bd, o = torch.topk(md, k, dim=1)
+        bi = torch.gather(mi, 1, o)
+    Ds, Is = D.index_select(0, sel), I.index_select(0, sel)
+    got, ref = Is.cpu().tolist(), bi.cpu().tolist()
+    recall = sum(len(set(a) & set(b)) for a, b in zip(got, ref)) / float(len(got) * k)
+    return {"queries": len(got), "recall": recall, "identical_ids": float((Is == bi).float().mean().item()),
+            "max_rel_err": float(((Ds - bd).abs() / bd.abs().clamp_min(1e-6)).max().item()),
+            "reference": "fp32 torch.matmul (TF32 off) + topk per shard over re-generated rows, all-gathered and merged"}
+
+
 def cpu_reference_run(torch, corpus_sample, q_sample, k, n_full):
     """One timed pass of the reference-equivalent CPU path on the sample; returns
     (seconds, queries/s scaled linearly to n_full rows)."""
@@ -291,6 +329,20 @@ def main():
     ms_e2e, _, _, _ = timed(step_host, args.steps)
     e2e_value = nq * args.steps / (ms_e2e / 1e3)
 
+    # ---- parity, outside the timed region: the (merged) result against an independent search ----
+    Dm, Im = step_device()
+    last = dict(store.last_search) if store is not None else {}
+    st_now = index.search_stats()
+    cert = torch.tensor([st_now["flagged_queries"], st_now["exact_queries"], st_now["refined_queries"]],
+                        dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(cert)                       # summed over the shards
+    parity = parity_check(torch, dist, world, rank, device, row0, row1, q_dev, k, Dm, Im)
+    parity.update(requeried=int(last.get("requeried", 0)), flagged=int(cert[0]), exact_queries=int(cert[1]),
+                  refined_queries=int(cert[2]))
+    if parity["recall"] < 0.999:
+        raise SystemExit(f"parity check failed: {parity}")
+
     # ---- roofline of the dominant kernel (the tcgen05 filter), timed live with CUDA events ----
     pk = peaks()
     n_local = row1 - row0
@@ -309,6 +361,8 @@ def main():
     if os.path.exists(tpath):   # dram bytes per corpus row from the committed ncu --set full capture
         roof["traffic"] = json.load(open(tpath))["dram_bytes_per_corpus_row"] * n_local
         roof["traffic_unit"] = "bytes per step (sum over the step's K1 launches; ncu dram read+write per row x rows)"
+        roof["traffic_source"] = ("constant from the committed ncu --set full capture (profiles/k1_traffic.json) "
+                                  "scaled by this rank's rows; NOT measured in this run")
         roof["algorithmic_bytes"] = n_local * DIM * 2 + nq * DIM * 2
     if roof["bound"] == "hbm":
         gbs = n_local * DIM * 2 / filt_s / 1e9 if filt_s > 0 else 0.0
@@ -346,6 +400,7 @@ def main():
                        "ctas_per_tile": stats["ctas_per_tile"], "kprime": stats["kprime"],
                        "corpus_chunks": stats["chunks"], "store_build_s": build_s},
             "roofline": roof,
+            "parity": parity,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12 * world,

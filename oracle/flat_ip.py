@@ -136,6 +136,27 @@ def flat_ip_search(corpus: np.ndarray, q: np.ndarray, k: int):
     return idx.search(q, k)
 
 
+def flat_ip_search_stream(blocks, q: np.ndarray, k: int):
+    """`IndexFlatIP.search` over a corpus that is handed over block by block —
+    `blocks` yields fp32 arrays [m_i, d] in id order — so a full-size corpus (8.8M x 768 = 27 GB)
+    never has to sit in host memory at once.  Same arithmetic and order as `flat_ip_search`."""
+    q = np.ascontiguousarray(q, dtype=np.float32)
+    Q = q.shape[0]
+    D = np.full((Q, k), FLT_LOWEST, dtype=np.float32)
+    I = np.full((Q, k), -1, dtype=np.int64)
+    base = 0
+    for xb in blocks:
+        xb = np.ascontiguousarray(xb, dtype=np.float32)
+        for r0 in range(0, xb.shape[0], 65536):
+            blk = xb[r0:r0 + 65536]
+            ids = np.arange(base + r0, base + r0 + blk.shape[0], dtype=np.int64)
+            bd, bi = _select_block(q @ blk.T, ids, k)
+            md, mi = np.concatenate([D, bd], axis=1), np.concatenate([I, bi], axis=1)
+            D, I = _merge_rows(md, mi, np.where(mi < 0, np.iinfo(np.int64).max, mi), k)
+        base += xb.shape[0]
+    return D, I
+
+
 def flat_ip_search_f64(corpus: np.ndarray, q: np.ndarray, k: int):
     """float64 brute force used to pin the fp32 oracle to the mathematical definition."""
     s = q.astype(np.float64) @ corpus.astype(np.float64).T

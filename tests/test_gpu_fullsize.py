@@ -1,11 +1,15 @@
-"""GPU (B200): BASELINE.json's full corpus size (8.8M x 768, the cfg2 / headline shape) checked
-through size-independent properties and an independent GPU fp32 reference on a query subset
-(SURVEY.md §8d "Parity at scale")."""
+"""GPU (B200): BASELINE.json's full corpus sizes checked through size-independent properties, an
+independent GPU fp32 reference on a fixed 512-query subset and the CPU oracle on 64 of those
+queries (SURVEY.md §8d "Parity at scale"); plus cfg1 in full against the CPU oracle."""
 import numpy as np
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
+
+from oracle import flat_ip  # noqa: E402
+
+SUB_GPU, SUB_CPU = 512, 64
 
 
 @pytest.fixture(scope="module")
@@ -20,10 +24,13 @@ def full_store():
     index = faiss_compat.IndexFlatIP(bench.DIM, device=0)
     bench.fill_rows(torch, index.add, 0, bench.HEADLINE["n"], dev)
     torch.cuda.synchronize()
-    return index
+    yield index
+    del index
+    torch.cuda.empty_cache()
 
 
 def _torch_reference(q, n, k):
+    """Independent exact search: fp32 torch.matmul (TF32 off) + topk over the same seeded chunks."""
     import bench
 
     torch.backends.cuda.matmul.allow_tf32 = False
@@ -40,6 +47,19 @@ def _torch_reference(q, n, k):
     return best_d, best_i
 
 
+def _assert_parity(D, I, Dr, Ir, k):
+    """north_star bar: scores within 1e-4 relative, ids identical except within-tolerance ties,
+    recall >= 0.999 — asserted at what the kernels deliver: 2e-5 on scores, and every differing
+    id sits in a tie at fp32 resolution of the two summation orders."""
+    D, I, Dr, Ir = (t.cpu().numpy() if torch.is_tensor(t) else t for t in (D, I, Dr, Ir))
+    recall = np.mean([len(set(a) & set(b)) / k for a, b in zip(I.tolist(), Ir.tolist())])
+    assert recall >= 0.999, recall
+    np.testing.assert_allclose(D, Dr, rtol=2e-5, atol=2e-4)
+    diff = I != Ir           # adjacent swaps between the two fp32 summation orders; denser at depth 1000
+    assert diff.mean() < (0.002 if k <= 200 else 0.01), diff.mean()
+    assert np.all(np.abs(D[diff] - Dr[diff]) <= 2e-5 * np.abs(Dr[diff]) + 2e-4)
+
+
 @pytest.mark.parametrize("k,nq", [(100, 1024), (1000, 512), (200, 700)])
 def test_full_corpus_parity_and_properties(full_store, k, nq):
     import bench
@@ -50,17 +70,19 @@ def test_full_corpus_parity_and_properties(full_store, k, nq):
     q = bench.make_queries(torch, nq, torch.device("cuda", 0))
     D, I = index.search(q, k)
     st = index.search_stats()
-    assert st["overflow_retries"] == 0 and st["flagged_queries"] == 0
+    assert st["overflow_retries"] == 0 and st["flagged_queries"] == 0 and st["exact_queries"] == 0
+    assert st["refined_queries"] <= nq // 100, st          # the default k' certifies in one pass
     assert (D[:, 1:] <= D[:, :-1]).all() and (I >= 0).all() and (I < n).all()
-    # no duplicate ids within a row
-    assert all(len(set(r.tolist())) == k for r in I[:16].cpu())
-    sub = 48
-    Dr, Ir = _torch_reference(q[:sub], n, k)
-    got = I[:sub].cpu()
-    recall = np.mean([len(set(Ir[r].tolist()) & set(got[r].tolist())) / k for r in range(sub)])
-    assert recall >= 0.999, recall                       # north_star: recall@k vs reference >= 0.999
-    torch.testing.assert_close(D[:sub], Dr, rtol=1e-4, atol=1e-3)   # scores within 1e-4 relative
-    assert (I[:sub] == Ir).float().mean() > 0.995        # ids identical except near-ties
+    assert all(len(set(r.tolist())) == k for r in I[:16].cpu())      # no duplicate ids within a row
+    # (i) independent GPU fp32 reference, fixed 512-query subset
+    Dr, Ir = _torch_reference(q[:SUB_GPU], n, k)
+    _assert_parity(D[:SUB_GPU], I[:SUB_GPU], Dr, Ir, k)
+    # (ii) the CPU oracle (numpy sgemm + canonical k-select), 64 queries, corpus streamed back
+    # from the store's fp32 plane in 2^19-row blocks
+    if k == 100:
+        blocks = (index.reconstruct_n(r0, min(1 << 19, n - r0)) for r0 in range(0, n, 1 << 19))
+        Dc, Ic = flat_ip.flat_ip_search_stream(blocks, q[:SUB_CPU].cpu().numpy(), k)
+        _assert_parity(D[:SUB_CPU], I[:SUB_CPU], Dc, Ic, k)
     # the 1-CTA and CTA-pair kernels agree bit for bit on ids and scores
     from denseretrievaltoolkits_b200 import _lib
 
@@ -80,3 +102,20 @@ def test_small_query_batch_is_hbm_bound_shape(full_store):
     Ds, Is = index.search(q[:16], 100)
     assert torch.equal(Is, I[:16]) and torch.equal(Ds, D[:16])
     assert index.search_stats()["ctas_per_tile"] == 1
+
+
+def test_cfg1_in_full_against_the_cpu_oracle():
+    """BASELINE cfg1: 1,000 queries x 100k x 768 fp32 passages, top-100 — the reference's own
+    CPU-runnable case, every query checked against the CPU oracle through the host (numpy) API."""
+    from denseretrievaltoolkits_b200.index import BaseFaissIPRetriever
+
+    x = torch.randn((100_000, 768), generator=torch.Generator().manual_seed(101)).numpy()
+    q = torch.randn((1000, 768), generator=torch.Generator().manual_seed(102)).numpy()
+    r = BaseFaissIPRetriever(x)
+    r.add(x)
+    D, I = r.search_with_scores(q, 100)
+    np.testing.assert_array_equal(r.search(q, 100), I)
+    Dc, Ic = flat_ip.flat_ip_search(x, q, 100)
+    _assert_parity(D, I, Dc, Ic, 100)
+    st = r.index.search_stats()
+    assert st["flagged_queries"] == 0 and st["exact_queries"] == 0

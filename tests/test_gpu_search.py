@@ -29,11 +29,13 @@ def _check_parity(D, I, Dr, Ir, k, n, scale):
     assert recall >= 0.999, recall
     valid = Ir >= 0
     np.testing.assert_array_equal(I >= 0, valid)
-    atol = RTOL * scale
-    np.testing.assert_allclose(D[valid], Dr[valid], rtol=RTOL, atol=atol)
+    # asserted at what the kernels deliver, not at the 1e-4 bar: 1e-5 relative plus the fp32
+    # rounding of two summation orders, 1e-6 |q||d| (scale = typical |q| = |d|)
+    rtol, atol = 1e-5, 1e-6 * scale * scale
+    np.testing.assert_allclose(D[valid], Dr[valid], rtol=rtol, atol=atol)
     diff = (I != Ir) & valid
     # a differing id must sit in a near-tie: the oracle's score at that rank equals ours within tol
-    assert np.all(np.abs(D[diff] - Dr[diff]) <= RTOL * np.abs(Dr[diff]) + atol)
+    assert np.all(np.abs(D[diff] - Dr[diff]) <= rtol * np.abs(Dr[diff]) + atol)
     assert (np.diff(D, axis=1) <= 0).all()
     assert ((I[:, kk:] == -1).all() and (D[:, kk:] == np.float32(-3.4028234663852886e38)).all())
     return recall
@@ -80,8 +82,8 @@ def test_search_matches_reference_wrapper_goldens(golden_dir, name):
         assert (I[:, 0] == 6).all() and 5 not in I and 7 not in I
         fin = np.isfinite(g["D"])
         same = (I == g["I"]) & fin
-        assert same[fin].mean() > 0.95
-        np.testing.assert_allclose(D[same], g["D"][same], rtol=RTOL, atol=1e-4)
+        assert same[fin].all()
+        np.testing.assert_allclose(D[same], g["D"][same], rtol=1e-5, atol=1e-5)
         return
     _check_parity(D, I, g["D"], g["I"], k, x.shape[0], scale=np.sqrt(64.0))
     if name in ("ties", "k_gt_n", "zeros"):
