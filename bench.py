@@ -288,7 +288,9 @@ def main():
 
     def step_host():
         if store is not None:
-            return store.search(q_np, k)
+            # every rank uploads its slice of the queries and downloads the result rows of that
+            # slice (the reference evaluates per rank, DRT/trainer/trainer.py:287-297)
+            return store.search(q_np, k, local_results=True)
         return index.search(q_np, k)
 
     def barrier():
@@ -403,9 +405,10 @@ def main():
             "parity": parity,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12 * world,
+                    "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12,
                     "note": "whole-job bytes: each query row crosses PCIe once (ranks upload 1/N slices and "
-                            "all-gather them over NVLink when N>1); every rank downloads the merged [nq,k] result"},
+                            "all-gather them over NVLink when N>1) and each merged result row is downloaded once, "
+                            "by the rank that owns that query slice (rank-local results)"},
             "gpu_launches": launches,
             "clocks": clocks,
             "search_stats": stats,

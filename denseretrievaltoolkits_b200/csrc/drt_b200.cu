@@ -159,9 +159,12 @@ struct drt_store {
     std::vector<Segment> segs;
     std::vector<float*> seg_f32;    // device pointer tables as the kernels take them (mirrors of segs)
     std::vector<float4*> seg_bound;
+    std::vector<float4*> seg_tile;
+    bool heavy_valid = false;       // per-segment `heavy` flags (select_kernel) are current
+    bool any_heavy = true;          // host copy: some segment is heavy (select tightens bounds per row)
     double margin_scale = 1.0;      // widens k' after searches in which the certificate flagged many queries
     // search workspace (grow-only)
-    DevBuf q_bf16, q_f32, thr, cnt, cand, seg_table, bound_table, qbound, out_scores, out_ids, misc;
+    DevBuf q_bf16, q_f32, thr, cnt, cand, seg_table, bound_table, tile_table, heavy, seg_valid, qbound, sel_scratch, out_scores, out_ids, misc;
     DevBuf qflag, sub_idx, sub_q, sub_os, sub_oi, sub_flag;   // exactness-check fallback
     int* err_host = nullptr;     // pinned + mapped: kernel watchdog code
     int* err_dev = nullptr;
@@ -203,6 +206,11 @@ int kprime_for(int k, double scale = 1.0) {
 // per padded query row than M=128 tiles (profiles/r1_q_sweep.md), but pad the query count to a
 // multiple of 256: pick the variant with the smaller padded cost.  With <= 128 queries half of
 // a pair tile would be padding and the pass is HBM-bound anyway.
+// Candidate buffer slots per query (8 B each) and the part of it select_kernel handles in shared
+// memory: 12 B per key, so 4096 keys leave room for four selecting CTAs per SM.
+constexpr int kCandCap = 16384;
+int select_capacity(int keep) { return keep <= 1024 ? 4096 : keep <= 2730 ? 8192 : 16384; }
+
 int default_ctas(int64_t nq) {
     const int64_t pad1 = (nq + drt::kTileM - 1) / drt::kTileM * drt::kTileM;
     const int64_t pad2 = (nq + 2 * drt::kTileM - 1) / (2 * drt::kTileM) * (2 * drt::kTileM);
@@ -215,8 +223,9 @@ int set_kernel_attrs(drt_store* s) {
                                   (int)drt::FilterCfg<1>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(drt::mips_filter_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)drt::FilterCfg<2>::kSmemBytes));
-    CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // 8192 keys + 8192 dims
     s->attrs_set = true;
     return DRT_OK;
 }
@@ -283,6 +292,7 @@ int ensure_segment(drt_store* s, int64_t seg, int64_t used, int64_t need, cudaSt
         s->segs.push_back(g);
         s->seg_f32.push_back(g.f32);
         s->seg_bound.push_back(g.bound);
+        s->seg_tile.push_back((float4*)g.tile);
     }
     Segment& cur = s->segs[seg];
     if (cur.cap < need) {
@@ -300,6 +310,7 @@ int ensure_segment(drt_store* s, int64_t seg, int64_t used, int64_t need, cudaSt
         cur = g;
         s->seg_f32[seg] = g.f32;
         s->seg_bound[seg] = g.bound;
+        s->seg_tile[seg] = (float4*)g.tile;
     }
     // a segment that starts (again) at row 0 -- new, or reused after reset -- has no tile maxima yet
     if (used == 0) CUDA_TRY(cudaMemsetAsync(cur.tile, 0, (size_t)(s->seg_rows / 256) * 16, st));
@@ -313,14 +324,16 @@ struct Chunk { int seg; int64_t row0, row1; };   // rows relative to the segment
 // `seen`, and a chunk of (growth-1)*seen further rows is expected to admit ~(growth-1)*keep
 // candidates per query, which must fit the candidate buffer.  attempt 2 uses fixed chunks of
 // (cap - keep) rows, which cannot overflow whatever the data order.
-std::vector<Chunk> plan_chunks(int64_t ntotal, int64_t seg_rows, int cap, int keep, int attempt) {
+// `sel` = candidates select_kernel handles in shared memory (its fast path), `cap` = slots of a
+// query's candidate buffer (>= sel; the rest is headroom against overflow retries).
+std::vector<Chunk> plan_chunks(int64_t ntotal, int64_t seg_rows, int sel, int cap, int keep, int attempt) {
     std::vector<Chunk> out;
     std::vector<int64_t> bounds;
     // Every row of the first chunk is admitted (thresholds start at -FLT_MAX), which costs the
     // epilogue's slow path per row: keep it at ~4 k' rows (enough for a k'-th score to exist).
-    // Later chunks grow by up to 16x: expected admissions (growth-1) k' stay below half the buffer.
-    int64_t first = std::max<int64_t>(256, (cap / 2) / 256 * 256);
-    int64_t growth = std::max<int64_t>(2, std::min<int64_t>(16, 1 + (cap - keep) / (2 * (int64_t)keep)));
+    // Later chunks grow by up to 16x: expected admissions (growth-1) k' stay below half of `sel`.
+    int64_t first = std::max<int64_t>(256, (sel / 2) / 256 * 256);
+    int64_t growth = std::max<int64_t>(2, std::min<int64_t>(16, 1 + (sel - keep) / (2 * (int64_t)keep)));
     if (attempt == 0) {
         // smallest first chunk (>= ~4 k') that still reaches the end of the first segment in as
         // few growth steps as the largest admissible one (cap / 2) would
@@ -362,9 +375,8 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                  int keep_override, unsigned char* qflag, int64_t* flagged_out) {
     const int dim = s->dim;
     const int keep = keep_override > 0 ? keep_override : kprime_for(k, s->margin_scale);
-    int cap = next_pow2(std::max(4 * keep, 4096));
-    if (attempt >= 1) cap *= 4;
-    if (cap > 16384) cap = 16384;        // select_kernel stages cap * 12 bytes in shared memory
+    const int sel = select_capacity(keep);
+    const int cap = kCandCap;
     if (cap < 2 * keep) return fail(DRT_E_UNSUPPORTED, "k=%d too large for the candidate buffer", k);
 
     int rc;
@@ -375,7 +387,11 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     if ((rc = s->misc.ensure(64)) != DRT_OK) return rc;
     if ((rc = s->seg_table.ensure(std::max<size_t>(8, s->seg_f32.size() * sizeof(float*)))) != DRT_OK) return rc;
     if ((rc = s->bound_table.ensure(std::max<size_t>(8, s->seg_bound.size() * sizeof(float4*)))) != DRT_OK) return rc;
+    if ((rc = s->tile_table.ensure(std::max<size_t>(8, s->seg_tile.size() * sizeof(float4*)))) != DRT_OK) return rc;
+    if ((rc = s->heavy.ensure(std::max<size_t>(8, s->segs.size()))) != DRT_OK) return rc;
+    if ((rc = s->seg_valid.ensure(std::max<size_t>(8, s->segs.size() * 8))) != DRT_OK) return rc;
     if ((rc = s->qbound.ensure((size_t)nq * sizeof(float4))) != DRT_OK) return rc;
+    if ((rc = s->sel_scratch.ensure((size_t)nq * keep * 8)) != DRT_OK) return rc;
 
     float* thr = (float*)s->thr.p;
     uint32_t* cnt = (uint32_t*)s->cnt.p;
@@ -388,9 +404,28 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                              cudaMemcpyHostToDevice, st));
     CUDA_TRY(cudaMemcpyAsync(s->bound_table.p, s->seg_bound.data(), s->seg_bound.size() * sizeof(float4*),
                              cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(s->tile_table.p, s->seg_tile.data(), s->seg_tile.size() * sizeof(float4*),
+                             cudaMemcpyHostToDevice, st));
     const bool exact_pass = (kctas == 0);    // fp32 SIMT first pass (last-resort refinement)
     const float4* qbound = (const float4*)s->qbound.p;
     const float4* const* bound_table = (const float4* const*)s->bound_table.p;
+    const float4* const* tile_table = (const float4* const*)s->tile_table.p;
+    if (!s->heavy_valid) {     // rows were added since the last search: refresh the per-segment flags
+        std::vector<long long> valid(s->segs.size());
+        for (size_t g = 0; g < valid.size(); ++g)
+            valid[g] = std::max<int64_t>(0, std::min<int64_t>(s->seg_rows, s->ntotal - (int64_t)g * s->seg_rows));
+        CUDA_TRY(cudaMemcpyAsync(s->seg_valid.p, valid.data(), valid.size() * 8, cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st));    // `valid` is a stack-lived pageable source
+        drt::segment_heavy_kernel<<<(int)s->segs.size(), 256, 0, st>>>(tile_table, (int)(s->seg_rows / 256),
+                                                                      (const long long*)s->seg_valid.p, (unsigned char*)s->heavy.p);
+        std::vector<unsigned char> hv(s->segs.size());
+        CUDA_TRY(cudaMemcpyAsync(hv.data(), s->heavy.p, hv.size(), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        s->any_heavy = false;
+        for (unsigned char h : hv) s->any_heavy = s->any_heavy || h != 0;
+        s->heavy_valid = true;
+        s->stats[0] += 1;
+    }
     {
         // error-model constants of the certificate (mips_filter.cuh): the tensor core accumulates
         // dim/16 K=16 steps, each at worst 18 truncations of 2^-23 relative to the running
@@ -405,8 +440,26 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     CUtensorMap tmap_q;
     if (!exact_pass && (rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
 
-    const std::vector<Chunk> chunks = plan_chunks(s->ntotal, s->seg_rows, cap, keep, attempt);
+    const std::vector<Chunk> chunks = plan_chunks(s->ntotal, s->seg_rows, sel, cap, keep, attempt);
     if (keep_override == 0 && !exact_pass) s->stats[6] = (int64_t)chunks.size();
+    // `expect` = candidates a query is expected to hold at this select.  The shared-memory staging
+    // area is sized for ~1.5x that (not for the worst case `sel`): more selecting CTAs fit an SM,
+    // and a query that gathered more takes the kernel's global-memory path.
+    auto launch_select = [&](double expect) {
+        int keys = 1024;
+        while (keys < sel && keys < 1.5 * expect + 256) keys *= 2;
+        keys = std::min(keys, sel);
+        if (s->any_heavy)
+            drt::select_kernel<true><<<(int)nq, 256, (size_t)keys * 12, st>>>(
+                cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow, qbound, bound_table, tile_table,
+                (const unsigned char*)s->heavy.p, (uint32_t)s->seg_rows, (uint32_t)keys, (uint64_t*)s->sel_scratch.p);
+        else
+            drt::select_kernel<false><<<(int)nq, 256, (size_t)keys * 8, st>>>(
+                cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow, qbound, bound_table, tile_table,
+                (const unsigned char*)s->heavy.p, (uint32_t)s->seg_rows, (uint32_t)keys, (uint64_t*)s->sel_scratch.p);
+        s->stats[0] += 1;
+    };
+    int64_t seen_at_select = 0;      // rows scanned when the thresholds were last refreshed
     CUtensorMap tmap_d;
     int tmap_seg = -1;
     size_t n_timed = 0;
@@ -421,9 +474,8 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
             drt::exact_filter_kernel<C><<<grid, C::THREADS, 0, st>>>(
                 q_dev, (long long)nq, rows, (long long)nrows, dim, (uint32_t)((int64_t)c.seg * s->seg_rows + c.row0), thr,
                 cnt, cand, (uint32_t)cap, aligned16_ptr(q_dev) ? 1 : 0, qbound, s->seg_bound[c.seg] + c.row0);
-            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 12, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow,
-                                                                      qbound, bound_table, (uint32_t)s->seg_rows);
-            s->stats[0] += 2;
+            launch_select((double)sel);
+            s->stats[0] += 1;
             continue;
         }
         if (c.seg != tmap_seg) {
@@ -470,10 +522,15 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         const int64_t seen = (int64_t)c.seg * s->seg_rows + c.row1;
         const bool last = (&c == &chunks.back());
         if (!frozen || last) {
-            drt::select_kernel<<<(int)nq, 256, (size_t)cap * 12, st>>>(cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow,
-                                                                      qbound, bound_table, (uint32_t)s->seg_rows);
-            s->stats[0] += 1;
-            if (attempt == 0 && (double)keep * (double)(s->ntotal - seen) / (double)seen < (double)(cap - keep) / 8.0) frozen = true;
+            // candidates held now: all rows of the first chunk; later the k' survivors plus what the
+            // rows since the last refresh admitted against that (by now stale) threshold,
+            // ~k' (seen - seen_then) / seen_then
+            const double expect = seen_at_select == 0 ? (double)std::min<int64_t>(seen, cap)
+                                                      : (double)keep * (double)seen / (double)seen_at_select;
+            launch_select(attempt == 0 ? expect : (double)sel);
+            seen_at_select = seen;
+            // thresholds frozen: the final select must still find its candidates in shared memory
+            if (attempt == 0 && (double)keep * (double)(s->ntotal - seen) / (double)seen < (double)(sel - keep) / 2.0) frozen = true;
         }
         s->stats[0] += 1;
         s->stats[1] += 1;
@@ -488,7 +545,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         s->stats[0] += 1;
     }
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(s->misc_host, s->misc.p, 16, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s->misc_host, s->misc.p, 24, cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
         (void)cudaGetLastError();
@@ -503,6 +560,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     }
     if ((int)(s->misc_host[0] & 0xffffffff) != 0) return 1;   // overflow -> caller retries
     if (flagged_out) *flagged_out = (int64_t)s->misc_host[1];
+    s->stats[10] += (int64_t)s->misc_host[2];
     return DRT_OK;
 }
 
@@ -647,7 +705,7 @@ int drt_store_destroy(drt_store* s) {
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     for (Segment& g : s->segs) free_segment(g);
     s->q_bf16.release(); s->q_f32.release(); s->thr.release(); s->cnt.release(); s->cand.release();
-    s->seg_table.release(); s->out_scores.release(); s->out_ids.release(); s->misc.release();
+    s->seg_table.release(); s->bound_table.release(); s->tile_table.release(); s->heavy.release(); s->seg_valid.release(); s->qbound.release(); s->sel_scratch.release(); s->out_scores.release(); s->out_ids.release(); s->misc.release();
     s->qflag.release(); s->sub_idx.release(); s->sub_q.release(); s->sub_os.release(); s->sub_oi.release(); s->sub_flag.release();
     if (s->err_host) cudaFreeHost(s->err_host);
     if (s->misc_host) cudaFreeHost(s->misc_host);
@@ -687,6 +745,7 @@ int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device
                                                        (long long)off);
         CUDA_TRY(cudaGetLastError());
         s->ntotal += take;
+        s->heavy_valid = false;
         done += take;
     }
     if (!rows_on_device) CUDA_TRY(cudaStreamSynchronize(st));
@@ -710,6 +769,7 @@ int drt_store_reset(drt_store* s) {
     if (!s) return fail(DRT_E_INVALID, "store is NULL");
     std::lock_guard<std::mutex> lk(s->mu);
     s->ntotal = 0;
+    s->heavy_valid = false;
     return DRT_OK;
 }
 
@@ -820,10 +880,7 @@ int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_
     if (ntotal < 0 || seg_rows < 256 || seg_rows % 256 != 0 || k <= 0 || k > DRT_MAX_K || attempt < 0)
         return fail(DRT_E_INVALID, "bad plan arguments");
     const int keep = kprime_for(k);
-    int cap = next_pow2(std::max(4 * keep, 4096));
-    if (attempt >= 1) cap *= 4;
-    if (cap > 16384) cap = 16384;
-    const std::vector<Chunk> chunks = plan_chunks(ntotal, seg_rows, cap, keep, attempt);
+    const std::vector<Chunk> chunks = plan_chunks(ntotal, seg_rows, select_capacity(keep), kCandCap, keep, attempt);
     for (size_t i = 0; i < chunks.size() && (int)i < max_chunks && out; ++i) {
         out[3 * i] = chunks[i].seg; out[3 * i + 1] = chunks[i].row0; out[3 * i + 2] = chunks[i].row1;
     }
@@ -833,11 +890,8 @@ int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_
 int drt_plan_params(int k, int attempt, int* kprime, int* cap_out) {
     if (k <= 0 || k > DRT_MAX_K) return fail(DRT_E_INVALID, "bad k");
     const int keep = kprime_for(k);
-    int cap = next_pow2(std::max(4 * keep, 4096));
-    if (attempt >= 1) cap *= 4;
-    if (cap > 16384) cap = 16384;
     if (kprime) *kprime = keep;
-    if (cap_out) *cap_out = cap;
+    if (cap_out) *cap_out = kCandCap;
     return DRT_OK;
 }
 
@@ -887,7 +941,7 @@ int drt_merge_topk_peers(int n_lists, const float* const* scores, const int64_t*
     DeviceGuard g(device);
     drt::PeerPtrs p;
     for (int i = 0; i < n_lists; ++i) {
-        if (!scores[i] || !ids[i] || !out_scores[i] || !out_ids[i] || !truncated[i]) return fail(DRT_E_INVALID, "NULL peer pointer %d", i);
+        if (!scores[i] || !ids[i] || !truncated[i] || (!out_scores[i]) != (!out_ids[i])) return fail(DRT_E_INVALID, "NULL peer pointer %d", i);
         p.scores[i] = scores[i]; p.ids[i] = (const long long*)ids[i];
         p.out_scores[i] = out_scores[i]; p.out_ids[i] = (long long*)out_ids[i]; p.truncated[i] = truncated[i];
     }

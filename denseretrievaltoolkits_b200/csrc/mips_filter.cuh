@@ -56,7 +56,7 @@ struct FilterParams {
     const float4* qbound;   // [nq] per-query error-bound coefficients (A, B, C, -), see below
     const float4* tile_bound; // this segment's per-256-row-tile maxima of the row bounds (r, Dx, Dt, -)
     uint32_t* cnt;          // [nq] candidates appended so far (may exceed cap: overflow)
-    uint64_t* cand;         // [nq][cap] packed (ordered score << 32 | ~row)
+    uint64_t* cand;         // [nq][cap] packed (ordered UPPER-BOUND score << 32 | ~row)
     int* err;               // host-mapped watchdog flag
 };
 
@@ -85,8 +85,10 @@ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
 //     s_fp32(q,j)  <=  ub(q,j) := s~(q,j) + A r + B Dx + C Dt            (all roundings upward)
 // The first pass keeps, per query, the k' rows with the largest ub; every other row has
 // ub <= thr (the k'-th largest ub), so once the exact k-th score exceeds thr no other row can
-// belong to the top-k: a proof, not an estimate.  K1 tests against the 256-row tile maxima
-// (ub_tile >= ub_row: a superset is admitted), select_kernel re-evaluates ub per row.
+// belong to the top-k: a proof, not an estimate.  K1 works with the 256-row tile maxima
+// (ub_tile >= ub_row: still a bound, a superset is admitted) and stores ub_tile as the
+// candidate's score; for segments in which some tile mixes very different row norms
+// select_kernel tightens the bound to the row's own entry.
 constexpr float kBoundHuge = 1e30f;     // stands in for non-finite norms (keeps 0 * x finite)
 __device__ __forceinline__ float bound_term(const float4& qb, const float4& rb) {
     return __fmaf_ru(qb.x, rb.x, __fmaf_ru(qb.y, rb.y, __fmul_ru(qb.z, rb.z)));
@@ -132,7 +134,8 @@ __device__ __noinline__ void flush_staging(uint32_t my_stage, uint32_t n, const 
 
 // Filter 32 consecutive scores of one query (registers v) against thr.  `row_id0` is the store
 // row id of v[0]; only the first `nvalid` columns exist in the corpus.
-__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr, uint32_t row_id0,
+// A hit is staged with its tile-level upper bound s~ + et (rounded up) as the key's score.
+__device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr, float et, uint32_t row_id0,
                                              int nvalid, uint32_t my_stage, uint32_t& scnt,
                                              const FilterParams& p, int q) {
     // maxima of the four 8-column sub-blocks: the warp only walks a sub-block in which some
@@ -157,7 +160,7 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr,
                 for (int j = 8 * b; j < 8 * b + 8; ++j) {
                     const float f = __uint_as_float(v[j]);
                     const bool hit = (f > thr) && (j < nvalid);
-                    const uint64_t key = pack_key(f, row_id0 + j);
+                    const uint64_t key = pack_key(__fadd_ru(f, et), row_id0 + j);
                     if (hit) asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * kSlotStride), "l"(key) : "memory");
                     scnt += hit ? 1u : 0u;
                 }
@@ -326,7 +329,8 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 const float4 tb = __ldg(p.tile_bound + p.n_tile_begin + nt);
                 ptx::mbar_wait(tfull_bar(acc), acc_phase, p.err, 104);
                 ptx::tc_fence_after();
-                const float thr_eff = __fsub_rd(thr, bound_term(qb, tb));
+                const float et = bound_term(qb, tb);
+                const float thr_eff = __fsub_rd(thr, et);
 
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN + half * kColsPerWarp;
                 const uint32_t col0 = half * kColsPerWarp;
@@ -336,10 +340,10 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 for (int c = 0; c < kColsPerWarp / 32; c += 2) {
                     tmem_ld_wait_regs(va);
                     ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-                    filter_chunk(va, thr_eff, p.row_base + row0 + col0 + c * 32, valid_cols - static_cast<int>(col0) - c * 32, my_stage, scnt, p, qc);
+                    filter_chunk(va, thr_eff, et, p.row_base + row0 + col0 + c * 32, valid_cols - static_cast<int>(col0) - c * 32, my_stage, scnt, p, qc);
                     tmem_ld_wait_regs(vb);
                     if (c + 2 < kColsPerWarp / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                    filter_chunk(vb, thr_eff, p.row_base + row0 + col0 + (c + 1) * 32, valid_cols - static_cast<int>(col0) - (c + 1) * 32, my_stage, scnt, p, qc);
+                    filter_chunk(vb, thr_eff, et, p.row_base + row0 + col0 + (c + 1) * 32, valid_cols - static_cast<int>(col0) - (c + 1) * 32, my_stage, scnt, p, qc);
                 }
                 // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
                 ptx::tc_fence_before();

@@ -101,29 +101,55 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int dim, int split, uin
 }
 
 // K-select: one CTA per query.  If the query gathered more than `keep` candidates, keep the
-// `keep` with the largest UPPER-BOUND score ub = s~ + E(q,row) (ties: row asc) and publish the
-// keep-th ub as the new admission threshold.  Every row that was never admitted, or is dropped
-// here, has ub <= that threshold, hence an exact score <= it: the invariant K2's exactness
-// certificate rests on.  Chunks are visited in ascending row order and admission is strict (>).
+// `keep` with the largest UPPER-BOUND score (ties: row asc) and publish the keep-th ub as the new
+// admission threshold.  Every row that was never admitted, or is dropped here, has ub <= that
+// threshold, hence an exact score <= it: the invariant K2's exactness certificate rests on.
+// Chunks are visited in ascending row order and admission is strict (>).
 //
-// The candidate lists hold RAW first-pass scores; the per-row bound is gathered here (16 B per
-// candidate from the store's row-bound table), ub keys are formed in shared memory, and the
-// survivors are written back with their raw scores again.
+// K1 stored every candidate with its TILE-level bound.  In segments flagged `heavy` (some tile
+// mixes row norms more than 1.5x apart, e.g. one huge row among ordinary ones) the bound is
+// tightened here to the row's own entry — ub_row = RU(RU(ub_tile - E_tile) + E_row), still an
+// upper bound — so one outlier cannot fill the list with its 255 tile neighbours.  That costs a
+// 16-byte gather per candidate, which homogeneous corpora never pay.
 //
-// Selection is an MSD radix select on the packed 64-bit keys (8 bits per pass, 256-bin smem
-// histogram, warp-parallel suffix scan to locate the bin holding the keep-th largest key), O(n)
-// work per query instead of the O(n log^2 n) of a full sort; keys are unique (the row id is part
-// of the key), so exactly `keep` keys are >= the pivot.  Survivors are written back unordered:
-// neither the filter kernel nor later selects need order, and K2 sorts its own output.
+// Selection is an MSD radix select on the packed 64-bit keys: 8-bit digits (256-bin smem
+// histogram, one bin per thread, block-wide suffix scan to locate the bin holding the keep-th
+// largest key), starting at the highest bit in which the keys differ at all (scores of one query
+// share their sign / exponent bits: the leading digits would land in one bin).  O(n) work per
+// query; keys are unique (the row id is part of the key), so exactly `keep` keys are >= the
+// pivot.  Survivors are written back unordered: neither the filter kernel nor later selects need
+// order, and K2 sorts its own output.
+//
+// Fast path: up to `smem_keys` candidates are staged in shared memory.  A longer list
+// (thresholds frozen too early, adversarial row order) is selected straight from global memory
+// and compacted through a scratch row; the host sizes chunks so that this is the exception.
+__device__ __forceinline__ uint64_t tighten_key(uint64_t key, const float4& qb, const float4* const* seg_bound,
+                                                const float4* const* seg_tile, const unsigned char* seg_heavy,
+                                                uint32_t seg_rows) {
+    const uint32_t lo = static_cast<uint32_t>(key);
+    const uint32_t r = 0xFFFFFFFFu - lo;
+    const uint32_t seg = r / seg_rows;
+    if (!seg_heavy[seg]) return key;
+    const uint32_t local = r - seg * seg_rows;
+    const float et = bound_term(qb, __ldg(seg_tile[seg] + (local >> 8)));
+    const float er = bound_term(qb, __ldg(seg_bound[seg] + local));
+    const float ub = __fadd_ru(__fsub_ru(ordered_to_float(static_cast<uint32_t>(key >> 32)), et), er);
+    return (static_cast<uint64_t>(float_to_ordered(ub)) << 32) | lo;
+}
+
+// kTighten = false: no segment of the store is heavy, the stored keys are final (8 B per staged
+// key instead of 12, no per-candidate segment lookup).
+template <bool kTighten>
 __global__ void __launch_bounds__(256)
 select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t keep,
               int* overflow, const float4* __restrict__ qbound, const float4* const* __restrict__ seg_bound,
-              uint32_t seg_rows) {
-    extern __shared__ uint64_t s_keys[];             // [cap] ub keys, then [cap] raw ordered scores
-    uint32_t* s_raw = reinterpret_cast<uint32_t*>(s_keys + cap);
+              const float4* const* __restrict__ seg_tile, const unsigned char* __restrict__ seg_heavy,
+              uint32_t seg_rows, uint32_t smem_keys, uint64_t* scratch) {
+    extern __shared__ uint64_t s_keys[];             // [smem_keys] tightened keys, then [smem_keys] stored scores
+    uint32_t* s_orig = reinterpret_cast<uint32_t*>(s_keys + smem_keys);
     __shared__ uint32_t s_hist[256];
-    __shared__ uint32_t s_bin, s_need, s_bucket, s_out;
-    __shared__ uint64_t s_pivot;
+    __shared__ uint32_t s_bin, s_need, s_bucket, s_out, s_wsum[8];
+    __shared__ uint64_t s_pivot, s_or[8], s_and[8];
     const int q = blockIdx.x;
     const int tid = threadIdx.x;
     uint32_t n = cnt[q];
@@ -134,66 +160,92 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
     if (n <= keep) return;
     uint64_t* row = cand + static_cast<size_t>(q) * cap;
     const float4 qb = qbound[q];
+    const bool in_smem = n <= smem_keys;
+    // the lists keep the STORED (tile-level) keys, so tightening is applied afresh by every select
+    auto tight = [&](uint64_t stored) -> uint64_t {
+        return kTighten ? tighten_key(stored, qb, seg_bound, seg_tile, seg_heavy, seg_rows) : stored;
+    };
+    auto tkey = [&](uint32_t i) -> uint64_t { return in_smem ? s_keys[i] : tight(row[i]); };
+    // ---- stage / tighten, and find the bits in which the keys differ ----
+    uint64_t k_or = 0, k_and = ~0ull;
     for (uint32_t i = tid; i < n; i += blockDim.x) {
-        const uint64_t key = row[i];
-        const uint32_t lo = static_cast<uint32_t>(key), raw = static_cast<uint32_t>(key >> 32);
-        const uint32_t r = 0xFFFFFFFFu - lo;
-        const uint32_t seg = r / seg_rows;
-        const float4 rb = __ldg(seg_bound[seg] + (r - seg * seg_rows));
-        const float ub = __fadd_ru(ordered_to_float(raw), bound_term(qb, rb));
-        s_raw[i] = raw;
-        s_keys[i] = (static_cast<uint64_t>(float_to_ordered(ub)) << 32) | lo;
+        const uint64_t stored = row[i];
+        const uint64_t key = tight(stored);
+        if (in_smem) { s_keys[i] = key; if (kTighten) s_orig[i] = static_cast<uint32_t>(stored >> 32); }
+        k_or |= key; k_and &= key;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        k_or |= __shfl_xor_sync(0xffffffffu, k_or, o);
+        k_and &= __shfl_xor_sync(0xffffffffu, k_and, o);
+    }
+    if ((tid & 31) == 0) { s_or[tid >> 5] = k_or; s_and[tid >> 5] = k_and; }
     if (tid == 0) { s_need = keep; s_out = 0; }
-    uint64_t prefix = 0, mask = 0;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) { k_or |= s_or[w]; k_and &= s_and[w]; }
+    const uint64_t differ = k_or ^ k_and;              // n > keep >= 1 distinct keys: never 0
+    const int top = 63 - __clzll(static_cast<long long>(differ));
+    int shift = max(0, top - 7);                        // first digit = bits [shift, shift + 8)
+    uint64_t mask = (shift + 8 >= 64) ? 0ull : ~((1ull << (shift + 8)) - 1ull);
+    uint64_t prefix = k_and & mask;                     // bits above the first digit are common to all keys
     bool found = false;
-    for (int shift = 56; shift >= 0 && !found; shift -= 8) {
+    while (!found) {
         s_hist[tid] = 0;                 // blockDim.x == 256
         __syncthreads();
         for (uint32_t i = tid; i < n; i += blockDim.x) {
-            const uint64_t key = s_keys[i];
+            const uint64_t key = tkey(i);
             if ((key & mask) == prefix) atomicAdd(&s_hist[(key >> shift) & 0xFF], 1u);
         }
         __syncthreads();
-        if (tid < 32) {
-            // lane l owns bins [8l, 8l+8); suffix-scan the lane sums to find the bin (from the
-            // top) at which the running count reaches `need`
+        {
+            // thread t owns bin t; suffix-scan the counts to find the bin (from the top) at which
+            // the running count reaches `need`
             const uint32_t need = s_need;
-            uint32_t h[8], s = 0;
-#pragma unroll
-            for (int b = 0; b < 8; ++b) { h[b] = s_hist[tid * 8 + b]; s += h[b]; }
-            uint32_t v = s;
+            const uint32_t h = s_hist[tid];
+            uint32_t v = h;                          // inclusive suffix sum inside the warp
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const uint32_t t = __shfl_down_sync(0xffffffffu, v, o);
-                if (tid + o < 32) v += t;
+                if ((tid & 31) + o < 32) v += t;
             }
-            const uint32_t above = v - s;          // keys in bins of higher lanes
-            if (above < need && need <= above + s) {
-                uint32_t cum = above;
-#pragma unroll
-                for (int b = 7; b >= 0; --b) {
-                    if (cum < need && need <= cum + h[b]) { s_bin = tid * 8 + b; s_need = need - cum; s_bucket = h[b]; }
-                    cum += h[b];
-                }
-            }
+            if ((tid & 31) == 0) s_wsum[tid >> 5] = v;
+            __syncthreads();
+            uint32_t above = v - h;                  // keys in higher bins of this warp ...
+            for (int w = (tid >> 5) + 1; w < 8; ++w) above += s_wsum[w];   // ... and of higher warps
+            if (above < need && need <= above + h) { s_bin = tid; s_need = need - above; s_bucket = h; }
         }
         __syncthreads();
         prefix |= static_cast<uint64_t>(s_bin) << shift;
         mask |= 0xFFull << shift;
-        if (s_bucket == 1) {             // a single key carries this prefix: it is the pivot
+        if (s_bucket == 1 || shift == 0) {   // one key carries this prefix (always true at shift 0): the pivot
             for (uint32_t i = tid; i < n; i += blockDim.x) {
-                const uint64_t key = s_keys[i];
+                const uint64_t key = tkey(i);
                 if ((key & mask) == prefix) s_pivot = key;
             }
             found = true;
         }
         __syncthreads();
+        // the next digit may overlap bits already fixed when shift < 8: harmless, the overlapping
+        // bits are equal for every key that still matches the prefix
+        shift = max(0, shift - 8);
     }
-    const uint64_t pivot = found ? s_pivot : prefix;
-    for (uint32_t i = tid; i < n; i += blockDim.x) {
-        const uint64_t key = s_keys[i];
-        if (key >= pivot) row[atomicAdd(&s_out, 1u)] = (static_cast<uint64_t>(s_raw[i]) << 32) | (key & 0xFFFFFFFFull);
+    const uint64_t pivot = s_pivot;
+    if (in_smem) {
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            const uint64_t key = s_keys[i];
+            if (key >= pivot)
+                row[atomicAdd(&s_out, 1u)] = kTighten ? (static_cast<uint64_t>(s_orig[i]) << 32) | (key & 0xFFFFFFFFull) : key;
+        }
+    } else {
+        // compact through the scratch row (the list cannot be rewritten in place while it is read)
+        uint64_t* tmp = scratch + static_cast<size_t>(q) * keep;
+        for (uint32_t i = tid; i < n; i += blockDim.x) {
+            const uint64_t stored = row[i];
+            if (tight(stored) >= pivot) tmp[atomicAdd(&s_out, 1u)] = stored;
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < keep; i += blockDim.x) row[i] = tmp[i];
     }
     if (tid == 0) {
         cnt[q] = keep;
@@ -201,52 +253,99 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
     }
 }
 
+// Per-segment `heavy` flags for select_kernel: one CTA per segment scans the segment's tile table
+// (max residual, max norm, max tail norm, max 1/norm per 256-row tile).
+__global__ void __launch_bounds__(256)
+segment_heavy_kernel(const float4* const* __restrict__ seg_tile, int tiles_per_seg, const long long* __restrict__ seg_valid_rows,
+                     unsigned char* __restrict__ seg_heavy) {
+    __shared__ int s_any;
+    if (threadIdx.x == 0) s_any = 0;
+    __syncthreads();
+    const int seg = blockIdx.x;
+    const int tiles = static_cast<int>((seg_valid_rows[seg] + 255) >> 8);
+    int any = 0;
+    for (int t = threadIdx.x; t < tiles && t < tiles_per_seg; t += blockDim.x) {
+        const float4 tb = seg_tile[seg][t];
+        // tb.y = max |d|, tb.w = max 1/|d| over the tile: their product is max|d| / min|d|
+        if (!(tb.y * tb.w <= 1.5f)) any = 1;           // also true for NaN / inf (zero or non-finite rows)
+    }
+    if (any) atomicOr(&s_any, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) seg_heavy[seg] = static_cast<unsigned char>(s_any);
+}
+
 // K2: exact fp32 rescoring of the first-pass candidates + final ordering + output.
 // One CTA per query; each warp computes whole dot products (coalesced float4 row reads).
 // Replaces the fp32 exactness of faiss' sgemm for the rows that can still matter.
-__global__ void __launch_bounds__(256)
+//
+// The candidates are first ordered by their upper bound ub.  The best k of them (by ub) are
+// rescored; the smallest exact score among those is a lower bound tau_lb of the final k-th
+// score, so a remaining candidate is rescored only if its ub reaches tau_lb — one whose ub lies
+// below cannot enter the top-k.  For 768-d Gaussian-like data that skips ~1/4 of the fp32 row
+// gathers at k' = 2k (the kernel is a pure HBM gather: bytes are time).
+__device__ __forceinline__ float rescore_dot(const float4* __restrict__ x4, const float4* q4, int dim4, int lane) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = lane; j < dim4; j += 32) {
+        const float4 x = __ldg(x4 + j);
+        const float4 y = q4[j];
+        a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
+        a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
+    }
+    float acc = (a0 + a1) + (a2 + a3);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    return acc;
+}
+
+__global__ void __launch_bounds__(256, 6)
 rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t keep,
                const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
                int k, long long id_offset, float* out_scores, long long* out_ids,
                int do_rescore, unsigned long long* flagged, unsigned char* qflag, int check,
                const float* __restrict__ thr) {
     extern __shared__ uint64_t s_keys[];            // [P] then dim floats
+    __shared__ unsigned int s_taulb;                // min exact score of the best-k-by-ub (ordered encoding)
+    __shared__ unsigned int s_done;                 // rows actually rescored (statistics)
     const int q = blockIdx.x;
     const int n = static_cast<int>(min(min(cnt[q], cap), keep));
     const int P = next_pow2_dev(max(n, 1));
     float* s_q = reinterpret_cast<float*>(s_keys + next_pow2_dev(static_cast<int>(keep)));
     for (int j = threadIdx.x; j < dim; j += blockDim.x) s_q[j] = q_f32[static_cast<size_t>(q) * dim + j];
-    __syncthreads();
+    if (threadIdx.x == 0) { s_taulb = 0xFFFFFFFFu; s_done = 0u; }
 
     const uint64_t* row = cand + static_cast<size_t>(q) * cap;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = row[i];
+    for (int i = n + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = 0ull;
+    bitonic_sort_desc_u64(s_keys, P);               // by the stored upper bound
+
     if (do_rescore) {
         const float4* q4 = reinterpret_cast<const float4*>(s_q);
-        for (int i = warp; i < n; i += nwarps) {
-            const uint64_t key = row[i];
-            const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(key);
-            const uint32_t seg = r / seg_rows, local = r - seg * seg_rows;
-            const float4* x4 = reinterpret_cast<const float4*>(seg_f32[seg] + static_cast<size_t>(local) * dim);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            for (int j = lane; j < (dim >> 2); j += 32) {
-                const float4 x = __ldg(x4 + j);
-                const float4 y = q4[j];
-                a0 = fmaf(x.x, y.x, a0); a1 = fmaf(x.y, y.y, a1);
-                a2 = fmaf(x.z, y.z, a2); a3 = fmaf(x.w, y.w, a3);
+        const int kk = min(k, n);
+        for (int pass = 0; pass < 2; ++pass) {
+            const int lo = pass == 0 ? 0 : kk, hi = pass == 0 ? kk : n;
+            const unsigned int taulb = (pass == 1 && kk == k) ? s_taulb : 0u;   // no skipping without k exact scores
+            for (int i = lo + warp; i < hi; i += nwarps) {
+                const uint64_t key = s_keys[i];
+                if (static_cast<uint32_t>(key >> 32) < taulb) {      // ub below k exact scores: cannot enter
+                    if (lane == 0) s_keys[i] = 0ull;
+                    continue;
+                }
+                const uint32_t r = 0xFFFFFFFFu - static_cast<uint32_t>(key);
+                const uint32_t seg = r / seg_rows, local = r - seg * seg_rows;
+                const float acc = rescore_dot(reinterpret_cast<const float4*>(seg_f32[seg] + static_cast<size_t>(local) * dim),
+                                              q4, dim >> 2, lane);
+                if (lane == 0) {
+                    const bool ok = acc > -FLT_MAX;    // also false for NaN
+                    s_keys[i] = ok ? pack_key(acc, r) : 0ull;
+                    if (pass == 0) atomicMin(&s_taulb, ok ? float_to_ordered(acc) : 0u);
+                    atomicAdd(&s_done, 1u);
+                }
             }
-            float acc = (a0 + a1) + (a2 + a3);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0) {
-                const bool ok = acc > -FLT_MAX;    // also false for NaN
-                s_keys[i] = ok ? pack_key(acc, r) : 0ull;
-            }
+            __syncthreads();
         }
-    } else {
-        for (int i = threadIdx.x; i < n; i += blockDim.x) s_keys[i] = row[i];
+        bitonic_sort_desc_u64(s_keys, P);
     }
-    for (int i = n + threadIdx.x; i < P; i += blockDim.x) s_keys[i] = 0ull;
-    bitonic_sort_desc_u64(s_keys, P);
 
     for (int i = threadIdx.x; i < k; i += blockDim.x) {
         const uint64_t key = (i < P) ? s_keys[i] : 0ull;
@@ -274,6 +373,7 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
             }
         }
         if (flag) atomicAdd(flagged, 1ull);
+        if (do_rescore) atomicAdd(flagged + 1, static_cast<unsigned long long>(s_done));
         if (qflag) qflag[q] = flag ? 1 : 0;
     }
 }
@@ -334,7 +434,7 @@ exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __re
 // K6 ingest, one warp per row: fp32 row -> bf16 plane (round to nearest even) plus the row's entry
 // of the error-bound table rb = (|d - bf16(d)|, |d[0:split)|, |d[split:)|, 0), each rounded up,
 // and the component-wise maxima of the row's 256-row tile (atomicMax on the bit patterns of
-// non-negative floats).  Non-finite norms are stored as kBoundHuge.  HBM-bound: 4 B in, 2 B out
+// non-negative floats; the fourth component tracks max 1/|d|, i.e. the tile's smallest norm).  Non-finite norms are stored as kBoundHuge.  HBM-bound: 4 B in, 2 B out
 // per element, 16 B per row.
 __global__ void __launch_bounds__(256)
 ingest_rows_kernel(const float* __restrict__ plane, long long n, int dim, int split, uint2* __restrict__ bf16,
@@ -378,6 +478,8 @@ ingest_rows_kernel(const float* __restrict__ plane, long long n, int dim, int sp
             atomicMax(tb + 0, __float_as_uint(r));
             atomicMax(tb + 1, __float_as_uint(dx));
             atomicMax(tb + 2, __float_as_uint(dt));
+            const float nrm = sqrtf(s_x + s_t);
+            atomicMax(tb + 3, __float_as_uint(nrm > 0.f ? 1.f / nrm : __int_as_float(0x7f800000)));   // 1 / min norm
         }
     }
 }
@@ -594,9 +696,11 @@ merge_sorted_peers_kernel(PeerPtrs p, int G, long long q_begin, int k_in, int k_
     __syncthreads();
     const unsigned char tr = static_cast<unsigned char>(s_trunc);
     for (int g = 0; g < G; ++g) {
-        float* os = p.out_scores[g] + static_cast<size_t>(q) * k_out;
-        long long* oi = p.out_ids[g] + static_cast<size_t>(q) * k_out;
-        for (int i = threadIdx.x; i < k_out; i += blockDim.x) { os[i] = s_osc[i]; oi[i] = s_oid[i]; }
+        if (p.out_scores[g]) {          // NULL: that rank does not want this query's row (rank-local results)
+            float* os = p.out_scores[g] + static_cast<size_t>(q) * k_out;
+            long long* oi = p.out_ids[g] + static_cast<size_t>(q) * k_out;
+            for (int i = threadIdx.x; i < k_out; i += blockDim.x) { os[i] = s_osc[i]; oi[i] = s_oid[i]; }
+        }
         if (threadIdx.x == 0) p.truncated[g][q] = tr;
     }
 }

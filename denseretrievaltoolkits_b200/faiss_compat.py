@@ -143,7 +143,7 @@ class IndexFlatIP:
         buf = (ctypes.c_int64 * 12)()
         _lib.check(self._lib.drt_search_stats(self._h, buf), "search_stats")
         names = ["launches", "filter_launches", "overflow_retries", "kprime", "flagged_queries",
-                 "ctas_per_tile", "chunks", "filter_ns", "exact_queries", "refined_queries"]
+                 "ctas_per_tile", "chunks", "filter_ns", "exact_queries", "refined_queries", "rescored_rows"]
         return dict(zip(names, [int(v) for v in buf]))
 
     # ---- reconstruct ------------------------------------------------------------------------

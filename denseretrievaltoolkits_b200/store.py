@@ -116,19 +116,25 @@ class _PeerExchange:
         bad = b[offs[4]:offs[4] + Q]
         return (cD, cI, oD, oI, bad), offs
 
-    def merge(self, offs, Q: int, kl: int, k: int):
-        """Barrier, merge my query slice from the peers' lists into everyone's result, barrier."""
+    def my_slice(self, Q: int):
+        per = -(-Q // self.world)
+        q0 = min(self.rank * per, Q)
+        return q0, max(0, min(per, Q - q0))
+
+    def merge(self, offs, Q: int, kl: int, k: int, local_only: bool = False):
+        """Barrier, merge my query slice from the peers' lists into everyone's result (or, with
+        `local_only`, into mine alone — the flags still go to every rank), barrier."""
         import ctypes
 
         lib = _lib.load()
         W = self.world
         bases = [int(p) for p in self.hdl.buffer_ptrs]
         arr = lambda off: (ctypes.c_void_p * W)(*[b + off for b in bases])
-        per = -(-Q // W)
-        q0 = min(self.rank * per, Q)
-        qn = max(0, min(per, Q - q0))
+        out = (lambda off: (ctypes.c_void_p * W)(*[(b + off) if (not local_only or g == self.rank) else None
+                                                    for g, b in enumerate(bases)]))
+        q0, qn = self.my_slice(Q)
         self.hdl.barrier(channel=0)
-        _lib.check(lib.drt_merge_topk_peers(W, arr(offs[0]), arr(offs[1]), q0, qn, kl, k, arr(offs[2]), arr(offs[3]),
+        _lib.check(lib.drt_merge_topk_peers(W, arr(offs[0]), arr(offs[1]), q0, qn, kl, k, out(offs[2]), out(offs[3]),
                                             arr(offs[4]), self.device.index, _lib.current_stream_ptr(self.device.index)),
                    "merge_topk_peers")
         self.hdl.barrier(channel=0)
@@ -144,8 +150,11 @@ def shard_offsets(counts) -> list[int]:
 
 class ShardedCorpusStore:
     def __init__(self, d: int, group=None, device: Optional[int] = None, num_virtual_shards: int = 0,
-                 seg_rows: int = 0, index_factory: Optional[Callable] = None,
-                 merge_fn: Optional[Callable] = None):
+                 seg_rows: int = 0, _test_index_factory: Optional[Callable] = None,
+                 _test_merge_fn: Optional[Callable] = None):
+        # `_test_*`: hooks for the CPU (gloo) tests of the host logic only — they let a test stand
+        # in for the device index / merge kernel.  The product path never sets them.
+        index_factory, merge_fn = _test_index_factory, _test_merge_fn
         self.d = int(d)
         self.group = group
         self.distributed = dist.is_available() and dist.is_initialized() and num_virtual_shards == 0
@@ -278,37 +287,60 @@ class ShardedCorpusStore:
         last = S[:, :, -1]
         return ((last >= Dm[:, k - 1].unsqueeze(0)) & (last > _NEG)).any(0)
 
-    def search(self, q, k: int, flags: int = 0):
+    def search(self, q, k: int, flags: int = 0, local_results: bool = False):
         """Every rank passes the SAME queries (CLI / benchmark use) and receives the global
-        (D [Q,k], I [Q,k]).  Collective: all ranks must call with equal (Q, k)."""
+        (D [Q,k], I [Q,k]).  Collective: all ranks must call with equal (Q, k).
+
+        `local_results=True`: every rank receives only the rows of ITS slice of the queries
+        (`result_slice(Q)`; the reference evaluates per rank, trainer.py:287-297), so the merged
+        rows are not broadcast and only Q/W rows are downloaded per rank."""
         if self._offsets is None:
             self.finalize()
         host_in = isinstance(q, np.ndarray)
         dev = getattr(self.shards[0], "device", None)
-        if host_in and dev is not None and torch.cuda.is_available():
-            # host queries: the device path end to end, one D2H copy of the merged result (instead
-            # of bouncing every shard's candidates through host memory)
-            qd = self._upload_queries(np.ascontiguousarray(q, dtype=np.float32), dev)
-            Dm, Im = self.search(qd, k, flags)
-            return _to_host(dev, Dm, Im)
+        on_gpu = dev is not None and torch.cuda.is_available()
+        qd = self._upload_queries(np.ascontiguousarray(q, dtype=np.float32), dev) if (host_in and on_gpu) else q
+        Q = qd.shape[0]
         kl = self.local_depth(k)
-        Dm, Im, bad = self._search_merged(q, k, kl, flags)
+        local = bool(local_results) and self.distributed and self.world > 1
+        q0, qn = self.result_slice(Q) if local else (0, Q)
+        Dm, Im, bad, owned = self._search_merged(qd, k, kl, flags, local)
         self.last_search = {"local_depth": kl, "requeried": 0}
-        if bad is not None:
-            nbad = int(bad.sum().item())          # same value on every rank (computed from exchanged data)
-            if nbad:
-                idx = bad.nonzero().squeeze(1)
-                qt = torch.from_numpy(q) if host_in else q
-                qb = qt.index_select(0, idx.to(qt.device))
-                Db, Ib, _ = self._search_merged(qb.numpy() if host_in else qb, k, k, flags)
-                Dm[idx] = Db
-                Im[idx] = Ib
-                self.last_search["requeried"] = nbad
-                if 4 * nbad > Dm.shape[0]:
-                    self._reduce_depth = False     # row order correlates with the queries
+        to_host = host_in and on_gpu
+        host = None
+        if to_host:
+            # host API: the result rows and the re-query count travel together, ONE sync
+            nb = bad.sum(dtype=torch.int64).reshape(1) if bad is not None else torch.zeros(1, dtype=torch.int64, device=Dm.device)
+            host = _to_host(dev, Dm[q0:q0 + qn], Im[q0:q0 + qn], nb)
+            nbad = int(host[2][0])
+        else:
+            nbad = int(bad.sum().item()) if bad is not None else 0   # same value on every rank (computed from exchanged data)
+        if nbad:
+            idx = bad.nonzero().squeeze(1)
+            qt = torch.from_numpy(qd) if isinstance(qd, np.ndarray) else qd
+            qb = qt.index_select(0, idx.to(qt.device))
+            Db, Ib, _, _ = self._search_merged(qb.numpy() if isinstance(qd, np.ndarray) else qb, k, k, flags, False)
+            if not owned:
+                Dm, Im = Dm.clone(), Im.clone()
+            Dm[idx] = Db
+            Im[idx] = Ib
+            owned, host = True, None
+            self.last_search["requeried"] = nbad
+            if 4 * nbad > Dm.shape[0]:
+                self._reduce_depth = False     # row order correlates with the queries
+        if to_host:
+            return (host[0], host[1]) if host is not None else _to_host(dev, Dm[q0:q0 + qn], Im[q0:q0 + qn])
         if host_in:
-            return Dm.cpu().numpy(), Im.cpu().numpy()
-        return Dm, Im
+            return Dm[q0:q0 + qn].cpu().numpy(), Im[q0:q0 + qn].cpu().numpy()
+        if not owned:                          # the peer result region is reused by the next search
+            return Dm[q0:q0 + qn].clone(), Im[q0:q0 + qn].clone()
+        return Dm[q0:q0 + qn], Im[q0:q0 + qn]
+
+    def result_slice(self, Q: int):
+        """(first query, count) of the rows this rank keeps with `local_results=True`."""
+        per = -(-Q // self.world)
+        q0 = min(self.rank * per, Q)
+        return q0, max(0, min(per, Q - q0))
 
     # Exchange + merge as one kernel over peer-mapped memory (torch symmetric memory over NVLink /
     # NVSwitch) instead of NCCL all-gather / all-to-all + merge.  Default on for NCCL groups of up
@@ -334,22 +366,23 @@ class ShardedCorpusStore:
                     self._peer = peer
         return self._peer is not False and self.world * kl <= 8192 and k <= 4096 and k <= self.world * kl
 
-    def _search_merged(self, q, k: int, kl: int, flags: int):
+    def _search_merged(self, q, k: int, kl: int, flags: int, local: bool = False):
         """Depth-kl search of every shard, candidate exchange, merge to depth k.
-        Returns torch (D [Q,k], I [Q,k], truncated-mask [Q] or None when kl == k)."""
+        Returns torch (D [Q,k], I [Q,k], truncated-mask [Q] or None when kl == k, owned) —
+        `owned` False: D / I are views of the peer-exchange result region, valid until the next
+        search; with `local` only this rank's `result_slice` rows of D / I are filled."""
         if self.distributed and self._peer_ok(q, kl, k):
             (cD, cI, oD, oI, bad), offs = self._peer.views(q.shape[0], kl, k)
             self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags, out=(cD, cI))
-            self._peer.merge(offs, q.shape[0], kl, k)
-            # the result region is reused by the next search: hand out copies
-            return oD.clone(), oI.clone(), (bad.bool() if kl < k else None)
+            self._peer.merge(offs, q.shape[0], kl, k, local_only=local)
+            return oD, oI, (bad.bool() if kl < k else None), False
         if self.distributed:
             D, I = self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags)
             if isinstance(D, np.ndarray):
                 D, I = torch.from_numpy(D), torch.from_numpy(I)
                 if dist.get_backend(self.group) == "nccl":
                     D, I = D.cuda(self.shards[0].device), I.cuda(self.shards[0].device)
-            return self._exchange_and_merge(D, I, k, check=kl < k)
+            return self._exchange_and_merge(D, I, k, check=kl < k) + (True,)
         parts = [s.search(q, kl, id_offset=self._offsets[g], flags=flags) for g, s in enumerate(self.shards)]
         if isinstance(parts[0][0], np.ndarray):
             dev = getattr(self.shards[0], "device", None)
@@ -357,7 +390,7 @@ class ShardedCorpusStore:
             parts = [(to_t(d), to_t(i)) for d, i in parts]
         S = torch.stack([p[0] for p in parts])
         Dm, Im = self._merge(S, torch.stack([p[1] for p in parts]), k)
-        return Dm, Im, (self._truncated(S, Dm, k) if kl < k else None)
+        return Dm, Im, (self._truncated(S, Dm, k) if kl < k else None), True
 
     # candidate entries per rank above which the exchange switches from all-gather (every rank
     # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged
@@ -412,11 +445,11 @@ class ShardedCorpusStore:
         gets back the global top-k of its own queries."""
         if not self.distributed:
             return self.search(q_local, k)
-        qs = [torch.empty_like(q_local) for _ in range(self.world)]
-        dist.all_gather(qs, q_local.contiguous(), group=self.group)
-        D, I = self.search(torch.cat(qs, dim=0), k)
         n = q_local.shape[0]
-        return D[self.rank * n:(self.rank + 1) * n], I[self.rank * n:(self.rank + 1) * n]
+        qs = torch.empty((self.world * n,) + tuple(q_local.shape[1:]), dtype=q_local.dtype, device=q_local.device)
+        dist.all_gather_into_tensor(qs, q_local.contiguous(), group=self.group)
+        # rank r's queries are rows [r n, (r+1) n) of the gathered batch = its `result_slice`
+        return self.search(qs, k, local_results=True)
 
     # host query bytes above which a rank uploads only its 1/W slice over PCIe and the ranks
     # all-gather the slices over NVLink (every rank passes the same queries to `search`)

@@ -110,7 +110,8 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k,
  *  [7] summed device time of the MMA-filter launches in ns (DRT_SEARCH_TIME_KERNELS only)
  *  [8] queries that needed the exact fp32 first pass (last-resort refinement)
  *  [9] queries whose certificate failed after the FIRST pass (searched again with a larger k';
- *      [4] counts what is still uncertified after the whole ladder)           [10..11] reserved */
+ *      [4] counts what is still uncertified after the whole ladder)
+ *  [10] candidate rows whose fp32 row was actually read by the rescoring kernel   [11] reserved */
 int drt_search_stats(const drt_store* s, int64_t out[12]);
 
 /* Host-side planning, exposed for tests (no device needed).  drt_plan_params: k' (first-pass
@@ -139,6 +140,9 @@ int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t
  * queries [q_begin, q_begin + q_count) and a per-query flag "some full list's last score is not
  * strictly below the merged k_out-th" (the exactness check of a reduced per-shard depth) are
  * stored into EVERY rank's out_scores[g] / out_ids[g] ([nq][k_out]) / truncated[g] ([nq]).
+ * out_scores[g] / out_ids[g] may both be NULL: rank g then receives only the flags (rank-local
+ * results: every rank keeps just the rows of the queries it merged, the reference's per-rank
+ * evaluation, DRT/trainer/trainer.py:287-297).
  * The pointer tables are host arrays of n_lists (<= 16) device pointers valid on `device`.
  * The caller provides the cross-rank barriers before (lists complete) and after (results
  * complete).  Replaces all-gather + drt_merge_topk of store.py's NCCL path. */

@@ -53,7 +53,7 @@ def _worker(rank, world, port, out_dir):
     x[900:950] = x[100:150]                       # cross-shard exact ties
     q = rng.standard_normal((6, 32)).astype(np.float32)
     split = [0, 430, 1000]                        # uneven shards
-    st = ShardedCorpusStore(32, index_factory=lambda: _OracleIndex(32), merge_fn=_oracle_merge)
+    st = ShardedCorpusStore(32, _test_index_factory=lambda: _OracleIndex(32), _test_merge_fn=_oracle_merge)
     st.add(x[split[rank]:split[rank + 1]])
     offs = st.finalize()
     assert offs == split, offs
@@ -63,7 +63,7 @@ def _worker(rank, world, port, out_dir):
     # rows correlated with the queries: shard 0 owns the whole top-200 -> truncation check -> re-query
     xc = x.copy()
     xc[:430] *= 5.0
-    stc = ShardedCorpusStore(32, index_factory=lambda: _OracleIndex(32), merge_fn=_oracle_merge)
+    stc = ShardedCorpusStore(32, _test_index_factory=lambda: _OracleIndex(32), _test_merge_fn=_oracle_merge)
     stc.add(xc[split[rank]:split[rank + 1]])
     Dc, Ic = stc.search(q, 200)
     depthc = dict(stc.last_search)

@@ -149,7 +149,7 @@ def test_shard_depth_rule_and_peer_buffer_layout():
             self.ntotal += len(x)
 
     def store(sizes):
-        st = ShardedCorpusStore(8, num_virtual_shards=len(sizes), index_factory=_Fake)
+        st = ShardedCorpusStore(8, num_virtual_shards=len(sizes), _test_index_factory=_Fake)
         for g, n in enumerate(sizes):
             st.add(np.zeros((n, 8), np.float32), shard=g)
         st.finalize()

@@ -73,6 +73,20 @@ try:
     Dn, In = peer.search(q.cpu().numpy()[:997], 100)
     res["peer_numpy_ragged"] = bool(np.array_equal(In, full.search(q, 100)[1].cpu().numpy()[:997]))
     ok = ok and res["peer_numpy_ragged"]
+    # rank-local results: every rank keeps only its slice of the queries (device and host API)
+    Df, If = full.search(q, 100)
+    for st_, name in ((peer, "peer"), (store, "nccl")):
+        q0, qn = st_.result_slice(997)
+        Dl, Il = st_.search(q[:997], 100, local_results=True)
+        Dh, Ih = st_.search(q.cpu().numpy()[:997], 100, local_results=True)
+        same = bool(torch.equal(Il, If[q0:q0 + qn]) and torch.equal(Dl, Df[q0:q0 + qn]) and
+                    np.array_equal(Ih, If[q0:q0 + qn].cpu().numpy()) and np.array_equal(Dh, Df[q0:q0 + qn].cpu().numpy()))
+        res[f"{name}_local_results"] = same
+        ok = ok and same
+    per = nq // world
+    Dl, Il = peer.search_local_queries(q[rank * per:(rank + 1) * per].contiguous(), 100)
+    res["peer_local_queries"] = bool(torch.equal(Il, If[rank * per:(rank + 1) * per]))
+    ok = ok and res["peer_local_queries"]
 
     def timeit(st, reps=30):
         for _ in range(5):
