@@ -51,3 +51,39 @@ def test_evaluate_flow_matches_oracle_flow():
     want = reduce_metrics(o_all, eval_num)
     assert got == want and got["query_num"] == n_q
     assert got["Recall@5"] > 0.9                                      # the planted passage is found
+
+
+def test_deferred_search_equals_per_step_searches():
+    """Trainer.evaluate with eval_batch_size 16 (run.sh:30): queueing the encoder outputs of many
+    steps and searching once returns, per step, exactly what the per-step searches return."""
+    from denseretrievaltoolkits_b200 import faiss_compat
+    from denseretrievaltoolkits_b200.deferred import DeferredSearch
+    from denseretrievaltoolkits_b200.index import BaseFaissIPRetriever
+    from denseretrievaltoolkits_b200.store import ShardedCorpusStore
+
+    rng = np.random.default_rng(1)
+    n, d, k = 60000, 768, 100
+    emb = rng.standard_normal((n, d), dtype=np.float32)
+    steps = [torch.from_numpy(rng.standard_normal((16, d), dtype=np.float32)).cuda() for _ in range(40)]
+    steps.append(torch.from_numpy(rng.standard_normal((5, d), dtype=np.float32)).cuda())      # ragged last batch
+    index = faiss_compat.IndexFlatIP(d, device=0, seg_rows=1 << 14)
+    index.add(emb)
+    store = ShardedCorpusStore(d, num_virtual_shards=2, device=0, seg_rows=1 << 14)
+    store.add_split(torch.from_numpy(emb).cuda())
+    store.finalize()
+    retr = BaseFaissIPRetriever(emb)
+    retr.add(emb)
+    per_step = [index.search(q, k) for q in steps]
+    for target in (index, store, retr):
+        ds = DeferredSearch(target, k, max_queries=256)
+        got = list(ds.results(enumerate(steps)))
+        assert [t for t, _ in got] == list(range(len(steps)))
+        assert ds.searches == 3                                        # 645 queries: 256 + 256 + tail
+        for (_, (D, I)), (Dr, Ir) in zip(got, per_step):
+            assert torch.equal(I, Ir) and torch.equal(D, Dr)
+    # numpy batches through the host API
+    ds = DeferredSearch(index, k, max_queries=100)
+    got = list(ds.results((i, q.cpu().numpy()) for i, q in enumerate(steps[:10])))
+    for (_, (D, I)), (Dr, Ir) in zip(got, per_step):
+        np.testing.assert_array_equal(I, Ir.cpu().numpy())
+        np.testing.assert_array_equal(D, Dr.cpu().numpy())

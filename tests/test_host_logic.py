@@ -171,3 +171,34 @@ def test_shard_depth_rule_and_peer_buffer_layout():
     sizes = [6980 * 40 * 4, 6980 * 40 * 8, 6980 * 100 * 4, 6980 * 100 * 8, 6980]
     assert offs[0] == 0 and all(o % 256 == 0 for o in offs) and total % 256 == 0
     assert all(offs[i] + sizes[i] <= offs[i + 1] for i in range(4)) and offs[4] + sizes[4] <= total
+
+
+def test_deferred_search_returns_per_step_slices_in_order():
+    """DeferredSearch (batching Trainer.evaluate's per-step searches, trainer.py:287-297): same
+    rows as per-step calls, in submission order, one search per `max_queries`."""
+    from denseretrievaltoolkits_b200.deferred import DeferredSearch
+
+    rng = np.random.default_rng(3)
+    x = rng.standard_normal((500, 16)).astype(np.float32)
+
+    class Brute:
+        calls = 0
+
+        def search(self, q, k):
+            Brute.calls += 1
+            s = q @ x.T
+            I = np.argsort(-s, axis=1, kind="stable")[:, :k]
+            return np.take_along_axis(s, I, axis=1), I
+
+    steps = [rng.standard_normal((n, 16)).astype(np.float32) for n in (16, 16, 7, 16, 16, 3)]
+    ds = DeferredSearch(Brute(), k=5, max_queries=40)
+    got = list(ds.results((i, q) for i, q in enumerate(steps)))
+    assert [t for t, _ in got] == list(range(len(steps)))
+    assert Brute.calls == 2 and ds.searches == 2 and len(ds) == 0          # 55 queued -> flush at >= 40, then the tail
+    for (tag, (D, I)), q in zip(got, steps):
+        Dr, Ir = Brute().search(q, 5)
+        np.testing.assert_array_equal(I, Ir)
+        np.testing.assert_array_equal(D, Dr)
+    assert ds.flush() == []
+    with pytest.raises(RuntimeError):
+        ds.add(np.zeros(16, np.float32))
