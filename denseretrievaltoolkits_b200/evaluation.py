@@ -120,14 +120,20 @@ def _pool(workers: int) -> ProcessPoolExecutor:
     if st["pool"] is None or st["workers"] != workers:
         if st["pool"] is not None:
             st["pool"].shutdown(wait=False, cancel_futures=True)
-        st["pool"], st["workers"] = ProcessPoolExecutor(max_workers=workers), workers
+        # forkserver, not fork: the caller is a trainer process that holds a CUDA context and
+        # NCCL / watchdog threads, and forking a multi-threaded CUDA process can deadlock the
+        # children on inherited locks.  The workers only need this module.
+        import multiprocessing
+
+        st["pool"] = ProcessPoolExecutor(max_workers=workers, mp_context=multiprocessing.get_context("forkserver"))
+        st["workers"] = workers
     return st["pool"]
 
 
 def shutdown_pool() -> None:
     """Stop the worker processes `hits_matrix` keeps between calls."""
     if _POOL_STATE["pool"] is not None:
-        _POOL_STATE["pool"].shutdown(wait=True, cancel_futures=True)
+        _POOL_STATE["pool"].shutdown(wait=False, cancel_futures=True)      # never block interpreter exit
         _POOL_STATE["pool"], _POOL_STATE["workers"] = None, 0
 
 

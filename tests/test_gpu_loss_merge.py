@@ -185,6 +185,44 @@ def test_dense_mining_end_to_end():
         assert not ((neg[r].cpu().numpy() >= pb[r]) & (neg[r].cpu().numpy() < pe[r])).any()
 
 
+def test_cfg5_shaped_mining_top200_with_positive_exclusion_in_batches(tmp_path):
+    """BASELINE cfg5's shape at test size: depth num_negative + |positives| = 200 + up to 3, the
+    query stream cut into several internal batches, a row-sharded store underneath, positive
+    exclusion on the device, and the JSONL the reference's sampler reads (sampler.py:57-66)."""
+    import json
+
+    from denseretrievaltoolkits_b200.mining import mine_hard_negatives, write_negatives_jsonl
+    from denseretrievaltoolkits_b200.store import ShardedCorpusStore
+    from oracle import flat_ip
+
+    rng = np.random.default_rng(13)
+    n, nq, num_negative = 50_000, 300, 200
+    x = rng.standard_normal((n, 768), dtype=np.float32)
+    q = rng.standard_normal((nq, 768), dtype=np.float32)
+    pb = rng.integers(0, n - 4, size=nq).astype(np.int64)
+    pe = pb + rng.integers(1, 4, size=nq)
+    q += 2.0 * x[pb]                                 # positives sit at the top of the ranking
+    store = ShardedCorpusStore(768, num_virtual_shards=4, device=0, seg_rows=1 << 13)
+    store.add_split(torch.from_numpy(x).cuda())
+    store.finalize()
+    neg = mine_hard_negatives(store, torch.from_numpy(q).cuda(), torch.from_numpy(pb), torch.from_numpy(pe), num_negative,
+                              batch_size=128)        # 3 internal batches (128 + 128 + 44)
+    neg = neg.cpu().numpy()
+    depth = num_negative + int((pe - pb).max())
+    _, Ir = flat_ip.flat_ip_search(x, q, depth)
+    ref = omerge.filter_negatives(Ir, pb, pe, num_negative)
+    assert neg.shape == (nq, num_negative) and (neg >= 0).all()
+    assert (neg == ref).mean() > 0.999               # differing entries: fp32 near-ties at depth 200
+    assert not ((neg >= pb[:, None]) & (neg < pe[:, None])).any()
+    passages = {i: [int(i), int(i) + 1] for i in np.unique(neg)}
+    samples = [{"query": [int(r)], "positives": [[int(p)] for p in range(pb[r], pe[r])]} for r in range(nq)]
+    path = tmp_path / "bm25negatives"
+    write_negatives_jsonl(str(path), samples, neg, passages)
+    recs = [json.loads(line) for line in open(path, encoding="utf-8")]
+    assert len(recs) == nq and all(len(r["negatives"]) == num_negative for r in recs)
+    assert recs[17]["negatives"][0] == passages[int(neg[17, 0])] and recs[17]["positives"] == samples[17]["positives"]
+
+
 def test_tensor_core_loss_path_is_fp32_accurate(monkeypatch):
     """Large shapes run the logits / dx / dy contractions on tcgen05 through an exact 3-way bf16
     split (6 partial products, fp32 accumulation).  Scores must stay within the path's 1e-4

@@ -202,3 +202,27 @@ def test_deferred_search_returns_per_step_slices_in_order():
     assert ds.flush() == []
     with pytest.raises(RuntimeError):
         ds.add(np.zeros(16, np.float32))
+
+
+def test_write_negatives_jsonl_matches_the_reference_file_layout(tmp_path, golden_dir):
+    """f3: the mined-negatives file.  Golden = the bytes the reference's own BM25Negatives.save
+    wrote for these samples (sampler.py:89-99; its load_passages cache branch, sampler.py:57-66,
+    read them back in the generator).  `write_negatives_jsonl` must produce the same bytes, and the
+    reference's read loop (json.loads per line) must give back the records QPCollator consumes."""
+    import json
+
+    from denseretrievaltoolkits_b200.mining import write_negatives_jsonl
+
+    g = json.load(open(os.path.join(golden_dir, "mining_samples.json"), encoding="utf-8"))
+    out = tmp_path / "bm25negatives"
+    write_negatives_jsonl(str(out), g["samples"], np.asarray(g["neg_ids"], dtype=np.int64), g["passages"])
+    want = open(os.path.join(golden_dir, "bm25negatives.jsonl"), "rb").read()
+    assert out.read_bytes() == want
+    data = []
+    with open(out, "r", encoding="utf-8") as f:                      # sampler.py:61-64
+        for line in f.readlines():
+            data.append(json.loads(line))
+    assert len(data) == len(g["samples"])
+    for rec, smp, row in zip(data, g["samples"], g["neg_ids"]):
+        assert rec["query"] == smp["query"] and rec["positives"] == smp["positives"]
+        assert rec["negatives"] == [g["passages"][j] for j in row if j >= 0]

@@ -9,6 +9,8 @@ are produced by running the reference's own importable code on seeded inputs:
                   faiss-shaped stub whose IndexFlatIP is oracle/flat_ip.py (faiss itself is not
                   installable here), plus a float64 brute force of the same inputs
   * search_factory_flat.npz  FaissRetriever (index.py:47-54) unmodified over the same stub
+  * bm25negatives.jsonl + mining_samples.json  the mined-negatives file as the reference's own
+                  BM25Negatives.save writes it and its load_passages cache branch reads it
   * mining.json   the loop of process_sample (DRT/trainer/sampler.py:73-78) restated verbatim
                   (the closure lives in a module that needs faiss at import time)
 Run:  python tools/make_golden.py        (needs /root/reference; tests never do)
@@ -176,6 +178,58 @@ def mining_goldens():
     print("mining cases", len(cases))
 
 
+def mining_jsonl_golden():
+    """The on-disk record layout of mined negatives: written by the reference's own
+    `BM25Negatives.save` (sampler.py:89-99) and read back by the cache branch of its
+    `load_passages` (sampler.py:57-66), both imported and run unmodified (faiss stubbed)."""
+    import shutil
+    import tempfile
+
+    stub = types.ModuleType("faiss")
+    stub.IndexFlatIP = flat_ip.IndexFlatIP
+    sys.modules.setdefault("faiss", stub)
+    import DRT.trainer.sampler as sampler_mod
+    from DRT.trainer.sampler import BM25Negatives
+
+    # upstream bug: load_passages returns `ListDataset(data)` (sampler.py:99), a name that is not
+    # defined anywhere (the class in that file is BM25Dataset, sampler.py:12-20) -> NameError after
+    # the file was read.  Bind the name so the reference's own read loop can be run.
+    sampler_mod.ListDataset = sampler_mod.BM25Dataset
+
+    rng = np.random.default_rng(41)
+    passages = [[int(t) for t in rng.integers(1000, 30000, size=int(rng.integers(5, 12)))] for _ in range(60)]
+    passages[7] = [101, 2054, 2003, 1996, 3007, 1997, 2605, 102]
+    samples, neg_ids = [], []
+    for i in range(9):
+        b = 5 * i
+        samples.append({"query": [int(t) for t in rng.integers(1000, 30000, size=6)],
+                        "positives": passages[b:b + 1 + i % 3]})
+        row = [int(v) for v in rng.choice(60, size=4, replace=False)]
+        if i % 4 == 0:
+            row[-1] = -1                        # fewer survivors than num_negative: padded with -1
+        neg_ids.append(row)
+    samples[3]["query"] = "naïve café — 東京"      # a text query: ensure_ascii=False on disk
+    expect = []
+    for smp, row in zip(samples, neg_ids):
+        rec = dict(smp)
+        rec["negatives"] = [passages[j] for j in row if j >= 0]
+        expect.append(rec)
+    tmp = tempfile.mkdtemp()
+    try:
+        obj = object.__new__(BM25Negatives)
+        obj.cache_dir = tmp
+        BM25Negatives.save(obj, expect, os.path.join(tmp, "BM25data"), "bm25negatives")
+        raw = open(os.path.join(tmp, "BM25data", "bm25negatives"), "rb").read()
+        loaded = BM25Negatives.load_passages(obj, corpus=None)            # cache branch: reads the file back
+        assert [loaded[i] for i in range(len(loaded))] == expect
+    finally:
+        shutil.rmtree(tmp)
+    open(os.path.join(OUT, "bm25negatives.jsonl"), "wb").write(raw)
+    json.dump(dict(samples=samples, neg_ids=neg_ids, passages=passages), open(os.path.join(OUT, "mining_samples.json"), "w"),
+              ensure_ascii=False)
+    print("mining jsonl golden:", len(expect), "records,", len(raw), "bytes")
+
+
 def eval_goldens():
     """has_answers (nq_eval.py:203-218) and get_metrics (metrics.py:50-59) run by the reference."""
     from DRT.evaluator.metrics import get_metrics
@@ -218,3 +272,4 @@ if __name__ == "__main__":
     metrics_goldens()
     search_goldens()
     mining_goldens()
+    mining_jsonl_golden()
