@@ -26,7 +26,7 @@ SYMBOLS = [
     "drt_store_device", "drt_store_reset", "drt_store_reconstruct", "drt_store_set_exact_tail",
     "drt_search", "drt_search_stats", "drt_plan_params", "drt_plan_chunks", "drt_merge_topk",
     "drt_merge_topk_peers",
-    "drt_inbatch_ce_fwd", "drt_inbatch_ce_bwd", "drt_filter_negatives",
+    "drt_inbatch_ce_fwd", "drt_inbatch_ce_bwd", "drt_inbatch_ce_bwd_needs_work", "drt_filter_negatives",
 ]
 
 SEARCH_DEFAULT = 0
@@ -103,6 +103,7 @@ def load() -> ctypes.CDLL:
     lib.drt_inbatch_ce_bwd.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                        c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p,
                                        c_void_p, c_void_p, c_int, c_void_p]
+    lib.drt_inbatch_ce_bwd_needs_work.argtypes = [c_int64, c_int64, c_int, c_int]
     lib.drt_filter_negatives.argtypes = [c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                                          c_void_p, c_int, c_void_p]
     for name in SYMBOLS:

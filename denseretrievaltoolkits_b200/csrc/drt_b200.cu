@@ -19,6 +19,7 @@
 #include "inbatch_ce.cuh"
 #include "mips_filter.cuh"
 #include "gemm_tc.cuh"
+#include "gemm_tc_small.cuh"
 #include "select_kernels.cuh"
 
 namespace {
@@ -957,14 +958,18 @@ int drt_merge_topk_peers(int n_lists, const float* const* scores, const int64_t*
 namespace {
 struct CeWorkspace {
     DevBuf part_max, part_sum, tgt, ticket;
-    DevBuf a_split, b_split, partials, logits;   // tensor-core path: bf16x3 operands, split-K partials
+    DevBuf a_split, b_split, a2_split, b2_split, partials, partials2, logits;   // tensor-core paths
     bool ticket_init = false;
     int* err_host = nullptr;
     int* err_dev = nullptr;
     bool tc_attrs = false;
 };
+// One workspace per (device, stream): two losses in flight on different streams of one device
+// (side streams, forward of step n+1 overlapping the backward of step n) never share tickets,
+// partial buffers or split operands.  Work on ONE stream is ordered by the stream itself.
 std::mutex g_ce_mu;
-std::map<int, CeWorkspace> g_ce_ws;
+std::map<std::pair<int, void*>, CeWorkspace> g_ce_ws;
+constexpr int kTicketSlots = 4096;       // [0] launch-wide ticket, [64 ..] per-tile tickets (two problems)
 }  // namespace
 
 extern "C++" {
@@ -1021,7 +1026,7 @@ void launch_ce_dlogits(const float* x, const float* y, long long B, long long P,
                                                                    grad_scale, work, vec_ok);
 }
 
-// ---- tensor-core (bf16x3 split) GEMM for the large loss shapes ------------------------------
+// ---- tensor-core (bf16x3 split) paths --------------------------------------------------------
 __global__ void sum_partials_kernel(const float* __restrict__ part, int S, long long n, float* __restrict__ C) {
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         float a = 0.f;
@@ -1030,19 +1035,33 @@ __global__ void sum_partials_kernel(const float* __restrict__ part, int S, long 
     }
 }
 
-inline bool tc_shape_ok(long long M, long long N, long long K) {
-    // worth the split + extra launches from ~256 x 2048 x 768 up (tools/ce_bench.py); K' = 6K must be a multiple of 64
-    static const double min_work = [] {
-        const char* e = getenv("DRT_B200_CE_TC_MIN");     // tuning knob: M*N*K above which the tensor-core path runs
-        return e ? atof(e) : 3.0e8;      // measured cross-over vs the SIMT core: 256 x 2048 x 768 already wins
+// Which path serves an [M, N] output contracted over K (all fp32-accurate):
+//   kPathSimt   odd shapes (K not a multiple of 4: the split operand's row pitch must be 16-byte aligned)
+//   kPathSmall  128 x 64 tiles + split-K, epilogue fused (gemm_tc_small.cuh): everything up to ~1e9 MACs
+//   kPathBig    128/256 x 256 persistent tiles (gemm_tc.cuh): cross-device negatives and larger
+enum { kPathSimt = 0, kPathSmall = 1, kPathBig = 2 };
+inline int ce_path(long long M, long long N, long long K) {
+    static const int forced = [] {
+        if (getenv("DRT_B200_CE_SIMT")) return (int)kPathSimt;
+        const char* e = getenv("DRT_B200_CE_PATH");        // tuning / test knob: simt | small | big
+        if (!e) return -1;
+        return !strcmp(e, "simt") ? (int)kPathSimt : !strcmp(e, "small") ? (int)kPathSmall : !strcmp(e, "big") ? (int)kPathBig : -1;
     }();
-    return K % 32 == 0 && (double)M * (double)N * (double)K >= min_work && M >= 128 && N >= 256;
+    if (K % 4 != 0 || K < 16) return kPathSimt;
+    if (forced == kPathSimt) return kPathSimt;
+    const bool big_ok = K % 32 == 0 && M >= 128 && N >= 256;
+    if (forced == kPathBig && big_ok) return kPathBig;
+    if (forced == kPathSmall) return kPathSmall;
+    static const double big_min = [] { const char* e = getenv("DRT_B200_CE_BIG_MIN"); return e ? atof(e) : 1.0e9; }();
+    return (big_ok && (double)M * (double)N * (double)K >= big_min) ? kPathBig : kPathSmall;
 }
 
-int ce_tc_setup(CeWorkspace& w) {
+int ce_tc_setup(CeWorkspace& w, cudaStream_t st) {
     if (!w.tc_attrs) {
         CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_nt_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::GemmTcCfg<1>::kSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::GemmTcCfg<2>::kSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_small_kernel<drt::kStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::kSmallSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_small_kernel<drt::kCe>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::kSmallSmemBytes));
         if (cudaHostAlloc((void**)&w.err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer((void**)&w.err_dev, w.err_host, 0) != cudaSuccess) {
             (void)cudaGetLastError();
@@ -1051,23 +1070,28 @@ int ce_tc_setup(CeWorkspace& w) {
         *w.err_host = 0;
         w.tc_attrs = true;
     }
+    int rc;
+    if ((rc = w.ticket.ensure(kTicketSlots * 4)) != DRT_OK) return rc;
+    if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, kTicketSlots * 4, st)); w.ticket_init = true; }
     return DRT_OK;
 }
 
 // C[M,N] = A'[M,Kp] · B'[N,Kp]^T, A'/B' bf16 K-major (Kp = 6K, multiple of 64).  Split-K over
 // `ksplit` chunks when the output has too few tiles to fill the GPU; partials are summed.
+// `ce`: fused cross-entropy epilogue (no split-K; C may be NULL).
+struct BigCe { float* part_max; float* part_sum; float* tgt; const long long* target; long long target_stride; };
 int gemm_tc_nt(CeWorkspace& w, const void* a_split, const void* b_split, long long M, long long N, long long Kp,
-               float* C, cudaStream_t st) {
-    int rc = ce_tc_setup(w);
-    if (rc != DRT_OK) return rc;
+               float* C, cudaStream_t st, const BigCe* ce = nullptr) {
     const int kctas = M > drt::kTileM ? 2 : 1;
     const int clusters_max = 148 / kctas;
     const int m_tiles = (int)((M + drt::kTileM * kctas - 1) / (drt::kTileM * kctas));
     const int n_tiles = (int)((N + drt::kTileN - 1) / drt::kTileN);
     const int nkb = (int)(Kp / drt::kBlockK);
     int ksplit = 1;
-    if (m_tiles * n_tiles < clusters_max) ksplit = std::max(1, std::min(nkb / 16, (2 * clusters_max + m_tiles * n_tiles - 1) / (m_tiles * n_tiles)));
+    if (!ce && m_tiles * n_tiles < clusters_max)
+        ksplit = std::max(1, std::min(nkb / 16, (2 * clusters_max + m_tiles * n_tiles - 1) / (m_tiles * n_tiles)));
     CUtensorMap ta, tb;
+    int rc;
     if ((rc = make_tmap_bf16(&ta, a_split, (uint64_t)M, (uint64_t)Kp, drt::kTileM)) != DRT_OK) return rc;
     if ((rc = make_tmap_bf16(&tb, b_split, (uint64_t)N, (uint64_t)Kp, drt::kTileN / kctas)) != DRT_OK) return rc;
     float* out = C;
@@ -1080,6 +1104,9 @@ int gemm_tc_nt(CeWorkspace& w, const void* a_split, const void* b_split, long lo
         p.num_m_tiles = m_tiles; p.num_n_tiles = n_tiles; p.unit_tiles = 1;
         p.ksplit = ksplit; p.num_k_blocks = nkb;
         p.M = M; p.N = N; p.ldc = N; p.C = out; p.err = w.err_dev;
+        p.ce_part_max = ce ? ce->part_max : nullptr; p.ce_part_sum = ce ? ce->part_sum : nullptr;
+        p.ce_tgt_logit = ce ? ce->tgt : nullptr; p.ce_target = ce ? ce->target : nullptr;
+        p.ce_target_stride = ce ? ce->target_stride : 0;
         const int total = m_tiles * n_tiles * ksplit;
         const int clusters = std::max(1, std::min(clusters_max, total));
         cudaLaunchConfig_t cfg = {};
@@ -1103,6 +1130,43 @@ int gemm_tc_nt(CeWorkspace& w, const void* a_split, const void* b_split, long lo
 }
 
 inline int split_blocks(long long total) { return (int)std::min<long long>((total + 255) / 256, 148ll * 16); }
+
+// ---- small-shape path: split jobs + gemm_tc_small_kernel --------------------------------------
+drt::SplitJob make_job(const float* src, long long R, long long C, long long lds, void* dst, int is_b, int transpose,
+                       int kind, int& tile_cursor) {
+    drt::SplitJob j;
+    j.src = src; j.R = R; j.C = C; j.lds = lds; j.dst = (__nv_bfloat16*)dst; j.is_b = is_b; j.transpose = transpose; j.kind = kind;
+    j.vec = (!transpose && C % 8 == 0 && lds % 4 == 0 && aligned16(src) && aligned16(dst)) ? 1 : 0;
+    j.tiles_x = (int)((C + (j.vec ? 63 : 31)) / (j.vec ? 64 : 32)); j.tiles_y = (int)((R + 31) / 32);
+    j.tile_begin = tile_cursor;
+    tile_cursor += j.tiles_x * j.tiles_y;
+    return j;
+}
+
+// Describes C[M,N] = A'[M,6K]·B'[N,6K]^T for gemm_tc_small_kernel; `budget` = CTAs this problem may use.
+int small_problem(drt::SmallProblem& pb, CUtensorMap* ta, CUtensorMap* tb, const void* a_split, const void* b_split,
+                  long long M, long long N, long long K, float* C, DevBuf& partials, unsigned int* tickets, int budget) {
+    const long long Kp = 6 * K;
+    pb.m_tiles = (int)((M + drt::kTileM - 1) / drt::kTileM);
+    pb.n_tiles = (int)((N + drt::kSmallTileN - 1) / drt::kSmallTileN);
+    pb.num_k_blocks = (int)((Kp + drt::kBlockK - 1) / drt::kBlockK);
+    const int tiles = pb.m_tiles * pb.n_tiles;
+    // K-chunks per tile: fill the CTA budget, at least `min_kb` k-blocks (x 24 KB in flight) per chunk
+    static const int max_split = [] { const char* e = getenv("DRT_B200_CE_KSPLIT_MAX"); return e ? std::max(1, atoi(e)) : 32; }();
+    static const int min_kb = [] { const char* e = getenv("DRT_B200_CE_MIN_KB"); return e ? std::max(1, atoi(e)) : 4; }();
+    pb.ksplit = std::max(1, std::min(std::min(budget / std::max(1, tiles), pb.num_k_blocks / min_kb), max_split));
+    pb.M = M; pb.N = N; pb.C = C;
+    pb.tile_ticket = tickets;
+    pb.partials = nullptr;
+    int rc;
+    if (pb.ksplit > 1) {
+        if ((rc = partials.ensure((size_t)tiles * pb.ksplit * drt::kTileM * drt::kSmallTileN * 4)) != DRT_OK) return rc;
+        pb.partials = (float*)partials.p;
+    }
+    if ((rc = make_tmap_bf16(ta, a_split, (uint64_t)M, (uint64_t)Kp, drt::kTileM)) != DRT_OK) return rc;
+    if ((rc = make_tmap_bf16(tb, b_split, (uint64_t)N, (uint64_t)Kp, drt::kSmallTileN)) != DRT_OK) return rc;
+    return DRT_OK;
+}
 }  // namespace
 }  // extern "C++"
 
@@ -1117,20 +1181,62 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
     DeviceGuard g(device);
     cudaStream_t st = (cudaStream_t)stream;
     std::lock_guard<std::mutex> lk(g_ce_mu);
-    CeWorkspace& w = g_ce_ws[device];
-    if (tc_shape_ok(B, P, dim) && !getenv("DRT_B200_CE_SIMT")) {
-        // large shape: fp32-accurate logits on the tensor cores (bf16x3 split), then row-wise CE
-        float* lg = logits_out;
-        if (!lg) { if ((rc = w.logits.ensure((size_t)B * P * 4)) != DRT_OK) return rc; lg = (float*)w.logits.p; }
+    CeWorkspace& w = g_ce_ws[std::make_pair(device, stream)];
+    const int path = ce_path(B, P, dim);
+    const long long* tg = (const long long*)target;
+    if (path == kPathSmall) {
+        // one launch prepares both operands (exact bf16x3 split), one launch does the contraction,
+        // the split-K reduction and the cross entropy; logits are stored only when asked for
+        if ((rc = ce_tc_setup(w, st)) != DRT_OK) return rc;
         if ((rc = w.a_split.ensure((size_t)B * 6 * dim * 2)) != DRT_OK) return rc;
         if ((rc = w.b_split.ensure((size_t)P * 6 * dim * 2)) != DRT_OK) return rc;
-        if ((rc = w.ticket.ensure(64)) != DRT_OK) return rc;
-        if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, 64, st)); w.ticket_init = true; }
-        drt::split3_rows_kernel<<<split_blocks(B * dim), 256, 0, st>>>(x, B, dim, dim, (__nv_bfloat16*)w.a_split.p, 0);
-        drt::split3_rows_kernel<<<split_blocks(P * dim), 256, 0, st>>>(y, P, dim, dim, (__nv_bfloat16*)w.b_split.p, 1);
-        if ((rc = gemm_tc_nt(w, w.a_split.p, w.b_split.p, B, P, 6ll * dim, lg, st)) != DRT_OK) return rc;
-        drt::ce_rows_from_logits_kernel<<<(unsigned)B, 256, 0, st>>>(lg, B, P, (const long long*)target, (long long)(P / B), loss_scale,
-                                                                   lse_out, loss_rows, loss_out, (unsigned int*)w.ticket.p);
+        drt::SmallParams sp = {};
+        CUtensorMap ta, tb;
+        unsigned int* tickets = (unsigned int*)w.ticket.p;
+        if ((rc = small_problem(sp.prob[0], &ta, &tb, w.a_split.p, w.b_split.p, B, P, dim, logits_out, w.partials, tickets + 64, 148)) != DRT_OK) return rc;
+        const int tiles = sp.prob[0].m_tiles * sp.prob[0].n_tiles;
+        if (tiles > kTicketSlots - 64) return fail(DRT_E_UNSUPPORTED, "loss shape needs %d tiles on the small-tile path", tiles);
+        if ((rc = w.part_max.ensure((size_t)B * sp.prob[0].n_tiles * 4)) != DRT_OK) return rc;
+        if ((rc = w.part_sum.ensure((size_t)B * sp.prob[0].n_tiles * 4)) != DRT_OK) return rc;
+        if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
+        drt::SplitJobs js = {};
+        int cursor = 0;
+        js.job[0] = make_job(x, B, dim, dim, w.a_split.p, 0, 0, 0, cursor);
+        js.job[1] = make_job(y, P, dim, dim, w.b_split.p, 1, 0, 0, cursor);
+        js.n_jobs = 2;
+        drt::split3_jobs_kernel<<<cursor, 256, 0, st>>>(js);
+        sp.prob[1] = sp.prob[0];
+        sp.ctas0 = tiles * sp.prob[0].ksplit;
+        sp.err = w.err_dev;
+        sp.ce.target = tg; sp.ce.target_stride = P / B; sp.ce.loss_scale = loss_scale;
+        sp.ce.part_max = (float*)w.part_max.p; sp.ce.part_sum = (float*)w.part_sum.p; sp.ce.tgt_logit = (float*)w.tgt.p;
+        sp.ce.ticket = tickets; sp.ce.lse_out = lse_out; sp.ce.loss_rows = loss_rows; sp.ce.loss_out = loss_out;
+        if (const char* e = getenv("DRT_B200_CE_TRACE")) sp.dbg = (unsigned long long*)strtoull(e, nullptr, 0);   // dev: device buffer address
+        drt::gemm_tc_small_kernel<drt::kCe><<<sp.ctas0, drt::kSmallThreads, drt::kSmallSmemBytes, st>>>(ta, tb, ta, tb, sp);
+        CUDA_TRY(cudaGetLastError());
+        return DRT_OK;
+    }
+    if (path == kPathBig) {
+        // large shape: 128/256 x 256 persistent tiles; every epilogue thread keeps the online
+        // (max, sum-exp) of its row over its 128 columns, so no pass over the logits follows
+        if ((rc = ce_tc_setup(w, st)) != DRT_OK) return rc;
+        if ((rc = w.a_split.ensure((size_t)B * 6 * dim * 2)) != DRT_OK) return rc;
+        if ((rc = w.b_split.ensure((size_t)P * 6 * dim * 2)) != DRT_OK) return rc;
+        const int ncol = 2 * (int)((P + drt::kTileN - 1) / drt::kTileN);
+        if ((rc = w.part_max.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
+        if ((rc = w.part_sum.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
+        if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
+        drt::SplitJobs js = {};
+        int cursor = 0;
+        js.job[0] = make_job(x, B, dim, dim, w.a_split.p, 0, 0, 0, cursor);
+        js.job[1] = make_job(y, P, dim, dim, w.b_split.p, 1, 0, 0, cursor);
+        js.n_jobs = 2;
+        drt::split3_jobs_kernel<<<cursor, 256, 0, st>>>(js);
+        BigCe ce{(float*)w.part_max.p, (float*)w.part_sum.p, (float*)w.tgt.p, tg, (long long)(P / B)};
+        if ((rc = gemm_tc_nt(w, w.a_split.p, w.b_split.p, B, P, 6ll * dim, logits_out, st, &ce)) != DRT_OK) return rc;
+        drt::ce_fold_kernel<<<(unsigned)((B + 7) / 8), 256, 0, st>>>((const float*)w.part_max.p, (const float*)w.part_sum.p,
+                                                                     (const float*)w.tgt.p, B, P, ncol, tg, (long long)(P / B), loss_scale,
+                                                                     lse_out, loss_rows, loss_out, (unsigned int*)w.ticket.p);
         CUDA_TRY(cudaGetLastError());
         return DRT_OK;
     }
@@ -1140,10 +1246,9 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
     if ((rc = w.part_max.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
     if ((rc = w.part_sum.ensure((size_t)B * ncol * 4)) != DRT_OK) return rc;
     if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
-    if ((rc = w.ticket.ensure(64)) != DRT_OK) return rc;
-    if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, 64, st)); w.ticket_init = true; }
+    if ((rc = w.ticket.ensure(kTicketSlots * 4)) != DRT_OK) return rc;
+    if (!w.ticket_init) { CUDA_TRY(cudaMemsetAsync(w.ticket.p, 0, kTicketSlots * 4, st)); w.ticket_init = true; }
     const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
-    const long long* tg = (const long long*)target;
     if (tier == 2) launch_ce_fwd<drt::GemmHuge>(x, y, B, P, dim, tg, loss_scale, logits_out, w, lse_out, loss_rows, loss_out, vec_ok, st);
     else if (tier == 1) launch_ce_fwd<drt::GemmLarge>(x, y, B, P, dim, tg, loss_scale, logits_out, w, lse_out, loss_rows, loss_out, vec_ok, st);
     else launch_ce_fwd<drt::GemmSmall>(x, y, B, P, dim, tg, loss_scale, logits_out, w, lse_out, loss_rows, loss_out, vec_ok, st);
@@ -1151,11 +1256,18 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
     return DRT_OK;
 }
 
+int drt_inbatch_ce_bwd_needs_work(int64_t B, int64_t P, int dim, int have_logits) {
+    if (B <= 0 || P <= 0 || dim <= 0) return 1;
+    const bool small = have_logits && ce_path(B, P, dim) == kPathSmall && ce_path(B, dim, P) != kPathSimt &&
+                       ce_path(P, dim, B) != kPathSimt;
+    return small ? 0 : 1;
+}
+
 int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim, const int64_t* target,
                        const float* lse, const float* logits, const float* grad_rows, int grad_stride, float grad_scale,
                        float* work, float* dx, float* dy, int device, void* stream) {
     if (B <= 0 || P <= 0 || dim <= 0) return fail(DRT_E_INVALID, "bad shape");
-    if (!x || !y || !lse || !grad_rows || !work) return fail(DRT_E_INVALID, "NULL pointer");
+    if (!x || !y || !lse || !grad_rows) return fail(DRT_E_INVALID, "NULL pointer");
     if (grad_stride != 0 && grad_stride != 1) return fail(DRT_E_INVALID, "grad_stride must be 0 (scalar) or 1 (per row)");
     int rc = check_device_cached(device);
     if (rc != DRT_OK) return rc;
@@ -1163,8 +1275,62 @@ int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int
     cudaStream_t st = (cudaStream_t)stream;
     const int vec_ok = aligned16(x) && aligned16(y) && dim % 4 == 0;
     const long long* tg = (const long long*)target;
+    // dx[B,d] contracts over P, dy[P,d] over B: both must be splittable for a tensor-core path
+    const int pdx = ce_path(B, dim, P), pdy = ce_path(P, dim, B), pfw = ce_path(B, P, dim);
+    const bool small = logits && pfw == kPathSmall && pdx != kPathSimt && pdy != kPathSimt;
+    if (small) {
+        // Launch 1: dlogits from the kept logits, written directly as the split bf16 operands of
+        // both contractions (row-major for dx, transposed for dy), plus the splits of y^T and x^T.
+        // Launch 2: both GEMMs (two problems, one grid).  Nothing is written to `work` or `logits`.
+        std::lock_guard<std::mutex> lk(g_ce_mu);
+        CeWorkspace& w = g_ce_ws[std::make_pair(device, stream)];
+        if ((rc = ce_tc_setup(w, st)) != DRT_OK) return rc;
+        drt::SplitJobs js = {};
+        int cursor = 0, nj = 0;
+        if (dx) {
+            if ((rc = w.a_split.ensure((size_t)B * 6 * P * 2)) != DRT_OK) return rc;       // dL'  [B, 6P]
+            if ((rc = w.b_split.ensure((size_t)dim * 6 * P * 2)) != DRT_OK) return rc;     // yT'  [d, 6P]
+            js.job[nj++] = make_job(logits, B, P, P, w.a_split.p, 0, 0, 1, cursor);
+            js.job[nj++] = make_job(y, P, dim, dim, w.b_split.p, 1, 1, 0, cursor);
+        }
+        if (dy) {
+            if ((rc = w.a2_split.ensure((size_t)P * 6 * B * 2)) != DRT_OK) return rc;      // dLT' [P, 6B]
+            if ((rc = w.b2_split.ensure((size_t)dim * 6 * B * 2)) != DRT_OK) return rc;    // xT'  [d, 6B]
+            js.job[nj++] = make_job(logits, B, P, P, w.a2_split.p, 0, 1, 1, cursor);
+            js.job[nj++] = make_job(x, B, dim, dim, w.b2_split.p, 1, 1, 0, cursor);
+        }
+        if (nj == 0) return DRT_OK;
+        js.n_jobs = nj;
+        js.lse = lse; js.target = tg; js.target_stride = P / B; js.grad_rows = grad_rows; js.grad_stride = grad_stride; js.grad_scale = grad_scale;
+        drt::split3_jobs_kernel<<<cursor, 256, 0, st>>>(js);
+        drt::SmallParams sp = {};
+        CUtensorMap t[4];
+        unsigned int* tickets = (unsigned int*)w.ticket.p;
+        // CTA budget: dy (M = P rows) has many tiles and a short K, dx few tiles and a long K
+        const int dy_tiles = dy ? (int)(((P + 127) / 128) * ((dim + 63) / 64)) : 0;
+        const int dx_tiles = dx ? (int)(((B + 127) / 128) * ((dim + 63) / 64)) : 0;
+        if (dx_tiles + dy_tiles > kTicketSlots - 64) return fail(DRT_E_UNSUPPORTED, "loss shape needs too many tiles on the small-tile path");
+        int np = 0, ctas[2] = {0, 0};
+        if (dx) {
+            const int budget = std::max(dx_tiles, 148 - std::min(dy_tiles, 100));
+            if ((rc = small_problem(sp.prob[np], &t[2 * np], &t[2 * np + 1], w.a_split.p, w.b_split.p, B, dim, P, dx, w.partials, tickets + 64, budget)) != DRT_OK) return rc;
+            ctas[np] = dx_tiles * sp.prob[np].ksplit; ++np;
+        }
+        if (dy) {
+            const int budget = std::max(dy_tiles, 148 - ctas[0]);
+            if ((rc = small_problem(sp.prob[np], &t[2 * np], &t[2 * np + 1], w.a2_split.p, w.b2_split.p, P, dim, B, dy, w.partials2, tickets + 64 + dx_tiles, budget)) != DRT_OK) return rc;
+            ctas[np] = dy_tiles * sp.prob[np].ksplit; ++np;
+        }
+        if (np == 1) { sp.prob[1] = sp.prob[0]; t[2] = t[0]; t[3] = t[1]; }
+        sp.ctas0 = ctas[0];
+        sp.err = w.err_dev;
+        drt::gemm_tc_small_kernel<drt::kStore><<<ctas[0] + ctas[1], drt::kSmallThreads, drt::kSmallSmemBytes, st>>>(t[0], t[1], t[2], t[3], sp);
+        CUDA_TRY(cudaGetLastError());
+        return DRT_OK;
+    }
+    if (!work) return fail(DRT_E_INVALID, "this shape needs the B*P work buffer");
     const int tier = gemm_tier(B, P, 148);
-    if (logits) {    // forward kept the logits: dlogits is one elementwise pass (in place when work == logits)
+    if (logits) {    // forward kept the logits: dlogits is one elementwise pass into `work`
         const long long total = (long long)B * P;
         const int blocks = (int)std::min<long long>((total + 255) / 256, 148ll * 16);
         drt::ce_dlogits_from_logits_kernel<<<blocks, 256, 0, st>>>(logits, (long long)B, (long long)P, tg, (long long)(P / B), lse,
@@ -1172,14 +1338,13 @@ int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int
     } else if (tier == 2) launch_ce_dlogits<drt::GemmHuge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     else if (tier == 1) launch_ce_dlogits<drt::GemmLarge>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
     else launch_ce_dlogits<drt::GemmSmall>(x, y, B, P, dim, tg, lse, grad_rows, grad_stride, grad_scale, work, vec_ok, st);
-    const bool tc = !getenv("DRT_B200_CE_SIMT") && tc_shape_ok(B, dim, P) && tc_shape_ok(P, dim, B) && dim >= 256;
+    const bool tc = pdx == kPathBig && pdy == kPathBig && dim >= 256;
     if (tc) {
         std::lock_guard<std::mutex> lk(g_ce_mu);
-        CeWorkspace& w = g_ce_ws[device];
-        const size_t need = (size_t)std::max(B, P) * 6 * std::max<long long>(std::max(B, P), dim) * 2;
+        CeWorkspace& w = g_ce_ws[std::make_pair(device, stream)];
+        if ((rc = ce_tc_setup(w, st)) != DRT_OK) return rc;
         if ((rc = w.a_split.ensure((size_t)B * 6 * P * 2)) != DRT_OK) return rc;      // dL' / dLT' : B*6P == P*6B elements
         if ((rc = w.b_split.ensure((size_t)dim * 6 * std::max(B, P) * 2)) != DRT_OK) return rc;
-        (void)need;
         dim3 tb(32, 8);
         if (dx) {   // dx[B,d] = dL[B,P] · (yT)[d,P]^T
             drt::split3_rows_kernel<<<split_blocks(B * P), 256, 0, st>>>(work, B, P, P, (__nv_bfloat16*)w.a_split.p, 0);

@@ -18,6 +18,7 @@
 // accumulator stages, 8 epilogue warps, optional CTA pairs) with a store epilogue.
 #pragma once
 #include <cuda_bf16.h>
+#include <cfloat>
 #include "mips_filter.cuh"
 
 namespace drt {
@@ -30,8 +31,16 @@ struct GemmTcParams {
     int num_k_blocks;     // K' / 64 (all chunks)
     long long M, N;
     long long ldc;
-    float* C;
+    float* C;             // output (may be NULL in CE mode: the logits are then never stored)
     int* err;
+    // CE mode (ce_part_max != NULL, ksplit == 1): the epilogue thread that owns a row keeps an
+    // online (max, sum-exp) over its 128 columns of the tile and picks the target logit, so the
+    // cross entropy needs no second pass over the logits (ce_fold_kernel finishes per row)
+    float* ce_part_max;   // [M][2 * num_n_tiles]
+    float* ce_part_sum;
+    float* ce_tgt_logit;  // [M]
+    const long long* ce_target;
+    long long ce_target_stride;
 };
 
 template <int kCtas>
@@ -171,13 +180,33 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 const long long col0 = static_cast<long long>(nt) * kTileN + half * kColsPerWarp;
                 float* crow = p.C + (static_cast<long long>(sp) * p.M + row) * p.ldc;
                 const bool vec_ok = (p.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.C) & 15u) == 0);
+                const bool ce = p.ce_part_max != nullptr;
+                const long long tcol = (ce && row < p.M) ? (p.ce_target ? p.ce_target[row] : row * p.ce_target_stride) : -1;
+                float run_m = -FLT_MAX, run_s = 0.f;
 #pragma unroll 1
                 for (int c = 0; c < kColsPerWarp / 32; ++c) {
                     uint32_t v[32];
                     ptx::tmem_ld_32x32(taddr + c * 32, v);
                     tmem_ld_wait_regs(v);
                     const long long cc = col0 + c * 32;
-                    if (row < p.M) {
+                    if (ce && row < p.M) {
+                        float cm = -FLT_MAX;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cc + j < p.N) cm = fmaxf(cm, __uint_as_float(v[j]));
+                        const float nm = fmaxf(run_m, cm);
+                        float cs = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) if (cc + j < p.N) cs += expf(__uint_as_float(v[j]) - nm);
+                        run_s = run_s * expf(run_m - nm) + cs;
+                        run_m = nm;
+                        if (tcol >= cc && tcol < cc + 32) {
+                            float t = 0.f;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) if (cc + j == tcol) t = __uint_as_float(v[j]);
+                            p.ce_tgt_logit[row] = t;
+                        }
+                    }
+                    if (row < p.M && p.C) {
                         if (vec_ok && cc + 32 <= p.N) {
 #pragma unroll
                             for (int j = 0; j < 32; j += 4)
@@ -189,6 +218,11 @@ gemm_tc_nt_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                 if (cc + j < p.N) crow[cc + j] = __uint_as_float(v[j]);
                         }
                     }
+                }
+                if (ce && row < p.M) {
+                    const long long slot = row * (2ll * p.num_n_tiles) + 2 * nt + half;
+                    p.ce_part_max[slot] = run_m;
+                    p.ce_part_sum[slot] = run_s;
                 }
                 ptx::tc_fence_before();
                 __syncwarp();
@@ -254,6 +288,50 @@ __global__ void split3_transpose_kernel(const float* __restrict__ src, long long
             else      { d[0] = mid; d[R] = hi; d[2 * R] = lo; d[3 * R] = hi;  d[4 * R] = mid; d[5 * R] = hi; }
         }
     }
+}
+
+// Finishes the fused cross entropy of gemm_tc_nt_kernel's CE mode: folds the per-(row, column
+// block) partials (max, sum-exp) into lse / per-row loss — one warp per row — and the last CTA
+// (atomic ticket) adds the per-row losses in a fixed order into the scaled total.
+__global__ void __launch_bounds__(256)
+ce_fold_kernel(const float* __restrict__ part_max, const float* __restrict__ part_sum, const float* __restrict__ tgt_logit,
+               long long B, long long P, int ncol, const long long* __restrict__ target, long long target_stride,
+               float loss_scale, float* lse_out, float* loss_rows, float* loss_out, unsigned int* ticket) {
+    __shared__ bool s_last;
+    const int lane = threadIdx.x & 31;
+    const long long i = static_cast<long long>(blockIdx.x) * 8 + (threadIdx.x >> 5);
+    if (i < B) {
+        float m = -FLT_MAX;
+        for (int c = lane; c < ncol; c += 32) m = fmaxf(m, part_max[i * ncol + c]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+        float s = 0.f;
+        for (int c = lane; c < ncol; c += 32) s += part_sum[i * ncol + c] * expf(part_max[i * ncol + c] - m);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) {
+            const float lse = m + logf(s);
+            const long long tc = target ? target[i] : i * target_stride;
+            lse_out[i] = lse;
+            loss_rows[i] = (tc >= 0 && tc < P) ? lse - tgt_logit[i] : __int_as_float(0x7fc00000);
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1u);
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    __shared__ double s_red[256];
+    double local = 0.0;
+    for (long long r = threadIdx.x; r < B; r += blockDim.x) local += static_cast<double>(__ldcg(loss_rows + r));
+    s_red[threadIdx.x] = local;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) s_red[threadIdx.x] += s_red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { *loss_out = static_cast<float>(s_red[0] * static_cast<double>(loss_scale)); *ticket = 0u; }
 }
 
 // Row-wise cross entropy over stored logits (large-shape forward): one CTA per row, online

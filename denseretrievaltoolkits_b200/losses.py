@@ -19,6 +19,16 @@ from . import _lib
 
 _REDUCTIONS = ("mean", "sum", "none")
 _KEEP_LOGITS_BYTES = 1 << 30
+_NEEDS_WORK = {}
+
+
+def _needs_work(lib, B: int, P: int, d: int, have_logits: bool) -> bool:
+    """Does the backward of this shape want the [B,P] scratch (cached per shape)?"""
+    key = (B, P, d, have_logits)
+    v = _NEEDS_WORK.get(key)
+    if v is None:
+        v = _NEEDS_WORK[key] = bool(lib.drt_inbatch_ce_bwd_needs_work(B, P, d, 1 if have_logits else 0))
+    return v
 
 
 def _f32c(t: Tensor) -> Tensor:
@@ -68,7 +78,6 @@ class _InBatchCE(torch.autograd.Function):
         ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else lse, logits if logits is not None else lse)
         ctx.has_target = tgt is not None
         ctx.has_logits = logits is not None
-        ctx.logits_private = logits is not None and not want_logits      # may be overwritten in place
         ctx.reduction = reduction
         ctx.scale = scale
         ctx.in_dtypes = (x.dtype, y.dtype)
@@ -87,14 +96,16 @@ class _InBatchCE(torch.autograd.Function):
         dev = xc.device
         g = _f32c(grad_loss)
         per_row = ctx.reduction == "none"
-        work = logits if ctx.logits_private else torch.empty((B, P), dtype=torch.float32, device=dev)
+        # the saved logits are never written: a second backward over the same graph
+        # (retain_graph=True, two losses sharing the node) sees them unchanged
+        work = torch.empty((B, P), dtype=torch.float32, device=dev) if _needs_work(lib, B, P, d, ctx.has_logits) else None
         need_x, need_y = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         dx = torch.empty_like(xc) if need_x else None
         dy = torch.empty_like(yc) if need_y else None
         _lib.check(lib.drt_inbatch_ce_bwd(
             xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if ctx.has_target else None,
             lse.data_ptr(), logits.data_ptr() if ctx.has_logits else None, g.data_ptr(), 1 if per_row else 0, ctx.scale,
-            work.data_ptr(),
+            work.data_ptr() if work is not None else None,
             dx.data_ptr() if dx is not None else None, dy.data_ptr() if dy is not None else None,
             dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_bwd")
         if dx is not None and ctx.in_dtypes[0] is not torch.float32:
@@ -145,29 +156,36 @@ class _ShardedInBatchCE(torch.autograd.Function):
         lse = torch.empty((B,), dtype=torch.float32, device=dev)
         out = torch.empty((B + 1,), dtype=torch.float32, device=dev)
         base = out.data_ptr()
-        _lib.check(lib.drt_inbatch_ce_fwd(xc.data_ptr(), y_all.data_ptr(), B, world * P, d, target.data_ptr(), 1.0, None,
+        # kept for the backward (dlogits is then formed from them instead of a second contraction)
+        keep = B * world * P * 4 <= _KEEP_LOGITS_BYTES and any(ctx.needs_input_grad[:2])
+        logits = torch.empty((B, world * P), dtype=torch.float32, device=dev) if keep else None
+        _lib.check(lib.drt_inbatch_ce_fwd(xc.data_ptr(), y_all.data_ptr(), B, world * P, d, target.data_ptr(), 1.0,
+                                          logits.data_ptr() if keep else None,
                                           lse.data_ptr(), base, base + 4 * B, dev.index,
                                           _lib.current_stream_ptr(dev.index)), "inbatch_ce_fwd")
         total = out[B:].clone()
         dist.all_reduce(total, group=group)
         coef = (float(world) if scale_loss else 1.0) / float(world * B)    # mean over all rows (x world_size)
-        ctx.save_for_backward(xc, y_all, lse, target)
+        ctx.save_for_backward(xc, y_all, lse, target, logits if keep else lse)
+        ctx.has_logits = keep
         ctx.meta = (group, rank, world, P, coef, x.dtype, y.dtype)
         return (total * coef).reshape(())
 
     @staticmethod
     def backward(ctx, grad_loss: Tensor):
-        xc, y_all, lse, target = ctx.saved_tensors
+        xc, y_all, lse, target, logits = ctx.saved_tensors
         group, rank, world, P, coef, xdt, ydt = ctx.meta
         lib = _lib.load()
         B, d = xc.shape
         dev = xc.device
         g = _f32c(grad_loss).reshape(1)
-        work = torch.empty((B, world * P), dtype=torch.float32, device=dev)
+        work = (torch.empty((B, world * P), dtype=torch.float32, device=dev)
+                if _needs_work(lib, B, world * P, d, ctx.has_logits) else None)
         dx = torch.empty_like(xc)
         dy_all = torch.empty_like(y_all)
         _lib.check(lib.drt_inbatch_ce_bwd(xc.data_ptr(), y_all.data_ptr(), B, world * P, d, target.data_ptr(), lse.data_ptr(),
-                                          None, g.data_ptr(), 0, coef, work.data_ptr(), dx.data_ptr(), dy_all.data_ptr(),
+                                          logits.data_ptr() if ctx.has_logits else None, g.data_ptr(), 0, coef,
+                                          work.data_ptr() if work is not None else None, dx.data_ptr(), dy_all.data_ptr(),
                                           dev.index, _lib.current_stream_ptr(dev.index)), "inbatch_ce_bwd")
         dy = torch.empty((P, d), dtype=torch.float32, device=dev)
         dist.reduce_scatter_tensor(dy, dy_all, group=group)

@@ -169,9 +169,15 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
  * g_i = grad_scale * grad_rows[i * grad_stride]: grad_stride = 1 for a per-row upstream gradient
  * (reduction='none'), 0 when grad_rows points at ONE device float (reduction='mean'/'sum': the
  * scalar upstream gradient, grad_scale = 1/B or 1).  dx = dlogits·y, dy = dlogitsᵀ·x.  `work` is
- * a device scratch of B*P floats (holds dlogits).  `logits` = the forward's logits_out if it was
- * kept (dlogits is then one elementwise pass; `work` may alias it), or NULL to recompute the
- * logits tile by tile.  dx / dy may be NULL to skip that gradient. */
+ * a device scratch of B*P floats (holds dlogits; see drt_inbatch_ce_bwd_needs_work).  `logits` =
+ * the forward's logits_out if it was kept (dlogits is then one elementwise pass), or NULL to
+ * recompute the logits tile by tile.  Neither `logits` nor any other input is modified, so the
+ * backward may run any number of times over the same saved tensors (retain_graph).  dx / dy may
+ * be NULL to skip that gradient. */
+/* 1 if drt_inbatch_ce_bwd needs the `work` scratch for this shape, 0 if it may be NULL (the
+ * small-shape tensor-core path forms dlogits directly as split bf16 operands). Host-only. */
+int drt_inbatch_ce_bwd_needs_work(int64_t B, int64_t P, int dim, int have_logits);
+
 int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int dim,
                        const int64_t* target, const float* lse, const float* logits,
                        const float* grad_rows, int grad_stride, float grad_scale, float* work,

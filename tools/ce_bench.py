@@ -9,7 +9,7 @@ torch.backends.cuda.matmul.allow_tf32 = False
 dev = torch.device("cuda", 0)
 
 
-def timeit(fn, reps=200, warm=20):
+def timeit(fn, reps=int(os.environ.get("CE_REPS", "200")), warm=int(os.environ.get("CE_WARM", "20"))):
     for _ in range(warm):
         fn()
     torch.cuda.synchronize()
