@@ -24,6 +24,7 @@ import struct
 import numpy as np
 
 from . import _lib
+from ._nvtx import rng as _nvtx
 
 METRIC_INNER_PRODUCT = 0
 METRIC_L2 = 1
@@ -87,8 +88,9 @@ class IndexFlatIP:
                 if x.device.index != self._device:
                     raise RuntimeError(f"add: rows are on cuda:{x.device.index}, store is on cuda:{self._device}")
                 x = x.detach().to(torch.float32).contiguous()
-                _lib.check(self._lib.drt_store_add(self._h, x.data_ptr(), x.shape[0], 1,
-                                                   _lib.current_stream_ptr(self._device)), "add")
+                with _nvtx("drt.store_add"):
+                    _lib.check(self._lib.drt_store_add(self._h, x.data_ptr(), x.shape[0], 1,
+                                                       _lib.current_stream_ptr(self._device)), "add")
                 return
             x = x.detach().cpu().numpy()
         x = np.ascontiguousarray(x, dtype=np.float32)
@@ -122,9 +124,10 @@ class IndexFlatIP:
             else:
                 D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
                 I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
-            _lib.check(self._lib.drt_search(self._h, x.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), 1,
-                                            int(id_offset), int(flags),
-                                            _lib.current_stream_ptr(self._device)), "search")
+            with _nvtx("drt.search"):
+                _lib.check(self._lib.drt_search(self._h, x.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), 1,
+                                                int(id_offset), int(flags),
+                                                _lib.current_stream_ptr(self._device)), "search")
             return D, I
         if _is_torch_tensor(x):
             x = x.detach().numpy()
@@ -134,9 +137,10 @@ class IndexFlatIP:
         nq = x.shape[0]
         D = np.empty((nq, k), dtype=np.float32)
         I = np.empty((nq, k), dtype=np.int64)
-        _lib.check(self._lib.drt_search(self._h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data, 0,
-                                        int(id_offset), int(flags),
-                                        _lib.current_stream_ptr(self._device)), "search")
+        with _nvtx("drt.search_host"):
+            _lib.check(self._lib.drt_search(self._h, x.ctypes.data, nq, k, D.ctypes.data, I.ctypes.data, 0,
+                                            int(id_offset), int(flags),
+                                            _lib.current_stream_ptr(self._device)), "search")
         return D, I
 
     def search_stats(self) -> dict:

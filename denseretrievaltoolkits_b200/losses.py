@@ -16,6 +16,7 @@ from torch import Tensor, nn
 from torch import distributed as dist
 
 from . import _lib
+from ._nvtx import rng as _nvtx
 
 _REDUCTIONS = ("mean", "sum", "none")
 _KEEP_LOGITS_BYTES = 1 << 30
@@ -69,10 +70,11 @@ class _InBatchCE(torch.autograd.Function):
         scale = 1.0 / B if reduction == "mean" else 1.0
         stream = _lib.current_stream_ptr(dev.index)
         base = out.data_ptr()
-        rc = lib.drt_inbatch_ce_fwd(
-            xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if tgt is not None else None, scale,
-            logits.data_ptr() if logits is not None else None, base + 4 * (B + 1), base, base + 4 * B,
-            dev.index, stream)
+        with _nvtx("drt.inbatch_ce_fwd"):
+            rc = lib.drt_inbatch_ce_fwd(
+                xc.data_ptr(), yc.data_ptr(), B, P, d, tgt.data_ptr() if tgt is not None else None, scale,
+                logits.data_ptr() if logits is not None else None, base + 4 * (B + 1), base, base + 4 * B,
+                dev.index, stream)
         if rc != 0:
             _lib.check(rc, "inbatch_ce_fwd")
         ctx.save_for_backward(xc, yc, lse, tgt if tgt is not None else lse, logits if logits is not None else lse)

@@ -24,6 +24,7 @@ import torch
 import torch.distributed as dist
 
 from . import _lib
+from ._nvtx import rng as _nvtx
 
 _NEG = -3.4028234663852886e38     # faiss' "no result" score
 
@@ -87,6 +88,7 @@ class _PeerExchange:
         self.buf = None
         self.hdl = None
         self.cap = 0
+        self._ptr_cache = {}       # (offsets, local_only) -> the five ctypes pointer tables of one launch
 
     @staticmethod
     def _layout(Q: int, kl: int, k: int):
@@ -108,6 +110,7 @@ class _PeerExchange:
             self.buf = self._symm.empty(cap, dtype=torch.uint8, device=self.device)
             self.hdl = self._symm.rendezvous(self.buf, self.group)
             self.cap = cap
+            self._ptr_cache = {}
         b = self.buf
         cD = b[offs[0]:offs[0] + Q * kl * 4].view(torch.float32).view(Q, kl)
         cI = b[offs[1]:offs[1] + Q * kl * 8].view(torch.int64).view(Q, kl)
@@ -128,14 +131,18 @@ class _PeerExchange:
 
         lib = _lib.load()
         W = self.world
-        bases = [int(p) for p in self.hdl.buffer_ptrs]
-        arr = lambda off: (ctypes.c_void_p * W)(*[b + off for b in bases])
-        out = (lambda off: (ctypes.c_void_p * W)(*[(b + off) if (not local_only or g == self.rank) else None
-                                                    for g, b in enumerate(bases)]))
+        key = (tuple(offs), bool(local_only))
+        tabs = self._ptr_cache.get(key)
+        if tabs is None:
+            bases = [int(p) for p in self.hdl.buffer_ptrs]
+            arr = lambda off: (ctypes.c_void_p * W)(*[b + off for b in bases])
+            out = (lambda off: (ctypes.c_void_p * W)(*[(b + off) if (not local_only or g == self.rank) else None
+                                                        for g, b in enumerate(bases)]))
+            tabs = self._ptr_cache[key] = (arr(offs[0]), arr(offs[1]), out(offs[2]), out(offs[3]), arr(offs[4]))
         q0, qn = self.my_slice(Q)
         self.hdl.barrier(channel=0)
-        _lib.check(lib.drt_merge_topk_peers(W, arr(offs[0]), arr(offs[1]), q0, qn, kl, k, out(offs[2]), out(offs[3]),
-                                            arr(offs[4]), self.device.index, _lib.current_stream_ptr(self.device.index)),
+        _lib.check(lib.drt_merge_topk_peers(W, tabs[0], tabs[1], q0, qn, kl, k, tabs[2], tabs[3], tabs[4],
+                                            self.device.index, _lib.current_stream_ptr(self.device.index)),
                    "merge_topk_peers")
         self.hdl.barrier(channel=0)
 
@@ -374,7 +381,8 @@ class ShardedCorpusStore:
         if self.distributed and self._peer_ok(q, kl, k):
             (cD, cI, oD, oI, bad), offs = self._peer.views(q.shape[0], kl, k)
             self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags, out=(cD, cI))
-            self._peer.merge(offs, q.shape[0], kl, k, local_only=local)
+            with _nvtx("drt.exchange_merge_peers"):
+                self._peer.merge(offs, q.shape[0], kl, k, local_only=local)
             return oD, oI, (bad.bool() if kl < k else None), False
         if self.distributed:
             D, I = self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags)
@@ -382,7 +390,8 @@ class ShardedCorpusStore:
                 D, I = torch.from_numpy(D), torch.from_numpy(I)
                 if dist.get_backend(self.group) == "nccl":
                     D, I = D.cuda(self.shards[0].device), I.cuda(self.shards[0].device)
-            return self._exchange_and_merge(D, I, k, check=kl < k) + (True,)
+            with _nvtx("drt.exchange_merge_nccl"):
+                return self._exchange_and_merge(D, I, k, check=kl < k) + (True,)
         parts = [s.search(q, kl, id_offset=self._offsets[g], flags=flags) for g, s in enumerate(self.shards)]
         if isinstance(parts[0][0], np.ndarray):
             dev = getattr(self.shards[0], "device", None)
