@@ -401,6 +401,15 @@ def main():
                   refined_queries=int(cert[2]))
     if parity["recall"] < 0.999:
         raise SystemExit(f"parity check failed: {parity}")
+    phases = None
+    if store is not None:
+        ph = store.profile_phases(q_dev, k)
+        if ph is not None:       # max / min over ranks of the two phases (untimed extra steps)
+            t = torch.tensor([ph["local_search_ms"], ph["exchange_merge_ms"], -ph["local_search_ms"]], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            phases = {"local_search_ms_max": float(t[0]), "local_search_ms_min": float(-t[2]), "exchange_merge_ms_max": float(t[1]),
+                      "nvlink_bytes_read_per_rank": ph["nvlink_bytes_read"], "nvlink_bytes_written_per_rank": ph["nvlink_bytes_written"],
+                      "note": "CUDA events per rank over 5 untimed steps; exchange_merge includes waiting for the slowest rank"}
 
     # ---- roofline of the dominant kernel (the tcgen05 filter), timed live with CUDA events ----
     pk = peaks()
@@ -474,6 +483,7 @@ def main():
                        "corpus_chunks": stats["chunks"], "store_build_s": build_s},
             "roofline": roof,
             "parity": parity,
+            "multi_gpu_phases": phases,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "queries/s", "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": nq * DIM * 4, "d2h_bytes_per_step": nq * k * 12,

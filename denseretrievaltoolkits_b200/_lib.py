@@ -24,8 +24,8 @@ SYMBOLS = [
     "drt_abi_version", "drt_last_error", "drt_device_count",
     "drt_store_create", "drt_store_destroy", "drt_store_add", "drt_store_ntotal", "drt_store_dim",
     "drt_store_device", "drt_store_reset", "drt_store_reconstruct", "drt_store_set_exact_tail",
-    "drt_search", "drt_search_stats", "drt_plan_params", "drt_plan_chunks", "drt_merge_topk",
-    "drt_merge_topk_peers",
+    "drt_search", "drt_search_async", "drt_search_stats", "drt_plan_params", "drt_plan_chunks", "drt_merge_topk",
+    "drt_merge_topk_peers", "drt_merge_topk_peers2",
     "drt_inbatch_ce_fwd", "drt_inbatch_ce_bwd", "drt_inbatch_ce_bwd_needs_work", "drt_filter_negatives",
 ]
 
@@ -90,6 +90,7 @@ def load() -> ctypes.CDLL:
     lib.drt_store_reconstruct.argtypes = [c_void_p, c_int64, c_int64, c_void_p, c_int, c_void_p]
     lib.drt_search.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int,
                                c_int64, c_uint32, c_void_p]
+    lib.drt_search_async.argtypes = [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_int64, c_uint32, c_void_p, c_void_p]
     lib.drt_search_stats.argtypes = [c_void_p, i64p]
     lib.drt_plan_params.argtypes = [c_int, c_int, POINTER(c_int), POINTER(c_int)]
     lib.drt_plan_chunks.argtypes = [c_int64, c_int64, c_int, c_int, i64p, c_int]
@@ -97,6 +98,9 @@ def load() -> ctypes.CDLL:
                                    c_void_p, c_uint32, c_int, c_void_p]
     lib.drt_merge_topk_peers.argtypes = [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int64, c_int, c_int,
                                          POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_int, c_void_p]
+    lib.drt_merge_topk_peers2.argtypes = [c_int, POINTER(c_void_p), POINTER(c_void_p), c_int64, c_int64, c_int, c_int,
+                                          POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), c_void_p,
+                                          c_int, c_void_p]
     lib.drt_inbatch_ce_fwd.argtypes = [c_void_p, c_void_p, c_int64, c_int64, c_int, c_void_p,
                                        c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                        c_void_p]

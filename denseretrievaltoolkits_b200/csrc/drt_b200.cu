@@ -174,6 +174,10 @@ struct drt_store {
     bool attrs_set = false;
     std::vector<cudaEvent_t> ev;   // per-launch timing events (DRT_SEARCH_TIME_KERNELS)
     int64_t exact_queries = 0;     // queries of the last search that needed the exact fp32 first pass
+    unsigned char* async_status = nullptr;   // drt_search_async: device byte that receives "redo needed"
+    cudaEvent_t async_done = nullptr;         // recorded behind an asynchronous search
+    size_t async_timed = 0;                   // K1 launches of it that were bracketed by timing events
+    bool async_pending = false;               // its counters have not been collected yet
     mutable std::mutex mu;         // add / search / reset / reconstruct on one store are serialised
 };
 
@@ -546,6 +550,19 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         s->stats[0] += 1;
     }
     CUDA_TRY(cudaGetLastError());
+    if (s->async_status) {
+        // asynchronous search: no host round trip.  "Result not final" (candidate overflow, or a
+        // query the certificate flagged) is published on the device for the caller's merge step.
+        drt::publish_status_kernel<<<1, 32, 0, st>>>((const int*)s->misc.p, (const unsigned long long*)((char*)s->misc.p + 8), s->async_status);
+        CUDA_TRY(cudaMemcpyAsync(s->misc_host, s->misc.p, 24, cudaMemcpyDeviceToHost, st));
+        if (!s->async_done) CUDA_TRY(cudaEventCreateWithFlags(&s->async_done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventRecord(s->async_done, st));
+        if (keep_override == 0 && !exact_pass) { s->stats[3] = keep; s->stats[5] = kctas; }
+        s->async_timed = n_timed;
+        s->async_pending = true;
+        s->stats[0] += 1;
+        return DRT_OK;
+    }
     CUDA_TRY(cudaMemcpyAsync(s->misc_host, s->misc.p, 24, cudaMemcpyDeviceToHost, st));
     cudaError_t e = cudaStreamSynchronize(st);
     if (e != cudaSuccess) {
@@ -704,6 +721,7 @@ int drt_store_destroy(drt_store* s) {
     if (!s) return DRT_OK;
     DeviceGuard g(s->device);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    if (s->async_done) cudaEventDestroy(s->async_done);
     for (Segment& g : s->segs) free_segment(g);
     s->q_bf16.release(); s->q_f32.release(); s->thr.release(); s->cnt.release(); s->cand.release();
     s->seg_table.release(); s->bound_table.release(); s->tile_table.release(); s->heavy.release(); s->seg_valid.release(); s->qbound.release(); s->sel_scratch.release(); s->out_scores.release(); s->out_ids.release(); s->misc.release();
@@ -877,6 +895,34 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k, float* out_score
     return DRT_OK;
 }
 
+int drt_search_async(drt_store* s, const float* q, int64_t nq, int k, float* out_scores, int64_t* out_ids,
+                     int64_t id_offset, uint32_t flags, uint8_t* status_out, void* stream) {
+    if (!s) return fail(DRT_E_INVALID, "store is NULL");
+    if (nq <= 0 || k <= 0 || k > DRT_MAX_K) return fail(DRT_E_INVALID, "need nq > 0 and 0 < k <= DRT_MAX_K (nq=%lld k=%d)", (long long)nq, k);
+    if (!q || !out_scores || !out_ids || !status_out) return fail(DRT_E_INVALID, "NULL query/output/status pointer");
+    std::lock_guard<std::mutex> lk(s->mu);
+    if (nq > 16384 || s->dim_user != s->dim || !aligned16_ptr(q) || s->ntotal == 0)
+        return fail(DRT_E_UNSUPPORTED, "asynchronous search needs 1..16384 queries, a dim that is a multiple of 64, 16-byte aligned queries and a non-empty store");
+    int rc = check_device(s->device);
+    if (rc != DRT_OK) return rc;
+    DeviceGuard g(s->device);
+    if ((rc = set_kernel_attrs(s)) != DRT_OK) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (s->async_pending) { CUDA_TRY(cudaEventSynchronize(s->async_done)); s->async_pending = false; }   // misc_host is reused
+    for (int i = 0; i < 12; ++i) s->stats[i] = 0;
+    s->exact_queries = 0;
+    int kctas = default_ctas(nq);
+    if (const char* e = getenv("DRT_B200_CTAS")) kctas = (atoi(e) == 2) ? 2 : 1;
+    if (flags & DRT_SEARCH_FORCE_1CTA) kctas = 1;
+    if (flags & DRT_SEARCH_FORCE_2CTA) kctas = 2;
+    if ((rc = s->qflag.ensure((size_t)nq)) != DRT_OK) return rc;
+    s->async_status = status_out;
+    int64_t flagged = 0;
+    rc = search_batch(s, q, nq, k, out_scores, out_ids, id_offset, flags, st, /*attempt=*/0, kctas, 0, (unsigned char*)s->qflag.p, &flagged);
+    s->async_status = nullptr;
+    return rc;
+}
+
 int drt_plan_chunks(int64_t ntotal, int64_t seg_rows, int k, int attempt, int64_t* out, int max_chunks) {
     if (ntotal < 0 || seg_rows < 256 || seg_rows % 256 != 0 || k <= 0 || k > DRT_MAX_K || attempt < 0)
         return fail(DRT_E_INVALID, "bad plan arguments");
@@ -896,8 +942,25 @@ int drt_plan_params(int k, int attempt, int* kprime, int* cap_out) {
     return DRT_OK;
 }
 
-int drt_search_stats(const drt_store* s, int64_t out[12]) {
-    if (!s || !out) return fail(DRT_E_INVALID, "bad arguments");
+int drt_search_stats(const drt_store* cs, int64_t out[12]) {
+    if (!cs || !out) return fail(DRT_E_INVALID, "bad arguments");
+    drt_store* s = const_cast<drt_store*>(cs);
+    {
+        std::lock_guard<std::mutex> lk(s->mu);
+        if (s->async_pending) {      // counters of an asynchronous search: collect them now (waits for it)
+            DeviceGuard g(s->device);
+            CUDA_TRY(cudaEventSynchronize(s->async_done));
+            for (size_t i = 0; i < s->async_timed; ++i) {
+                float ms = 0.f;
+                if (cudaEventElapsedTime(&ms, s->ev[2 * i], s->ev[2 * i + 1]) == cudaSuccess) s->stats[7] += (int64_t)(ms * 1e6);
+            }
+            if ((int)(s->misc_host[0] & 0xffffffff) != 0) s->stats[2] += 1;
+            s->stats[9] += (int64_t)s->misc_host[1];
+            s->stats[4] += (int64_t)s->misc_host[1];     // flagged and NOT refined here: the caller redoes the search
+            s->stats[10] += (int64_t)s->misc_host[2];
+            s->async_pending = false;
+        }
+    }
     for (int i = 0; i < 12; ++i) out[i] = s->stats[i];
     out[8] = s->exact_queries;
     return DRT_OK;
@@ -931,12 +994,19 @@ int drt_merge_topk(int n_lists, const float* scores, const int64_t* ids, int64_t
 int drt_merge_topk_peers(int n_lists, const float* const* scores, const int64_t* const* ids, int64_t q_begin,
                          int64_t q_count, int k_in, int k_out, float* const* out_scores, int64_t* const* out_ids,
                          uint8_t* const* truncated, int device, void* stream) {
+    return drt_merge_topk_peers2(n_lists, scores, ids, q_begin, q_count, k_in, k_out, out_scores, out_ids, truncated, nullptr,
+                                 nullptr, device, stream);
+}
+
+int drt_merge_topk_peers2(int n_lists, const float* const* scores, const int64_t* const* ids, int64_t q_begin,
+                          int64_t q_count, int k_in, int k_out, float* const* out_scores, int64_t* const* out_ids,
+                          uint8_t* const* truncated, const uint8_t* const* status, uint8_t* redo, int device, void* stream) {
     if (n_lists <= 0 || n_lists > 16 || q_begin < 0 || q_count < 0 || k_in <= 0 || k_out <= 0)
         return fail(DRT_E_INVALID, "bad peer-merge shape");
     if (!scores || !ids || !out_scores || !out_ids || !truncated) return fail(DRT_E_INVALID, "NULL pointer table");
     if ((int64_t)n_lists * k_in > 8192 || k_out > 4096) return fail(DRT_E_UNSUPPORTED, "peer merge of %d x %d entries is too large", n_lists, k_in);
     if (k_out > n_lists * k_in) return fail(DRT_E_INVALID, "k_out=%d exceeds the %d merged entries", k_out, n_lists * k_in);
-    if (q_count == 0) return DRT_OK;
+    if (q_count == 0 && !status) return DRT_OK;
     int rc = check_device(device);
     if (rc != DRT_OK) return rc;
     DeviceGuard g(device);
@@ -947,8 +1017,15 @@ int drt_merge_topk_peers(int n_lists, const float* const* scores, const int64_t*
         p.out_scores[i] = out_scores[i]; p.out_ids[i] = (long long*)out_ids[i]; p.truncated[i] = truncated[i];
     }
     for (int i = n_lists; i < 16; ++i) { p.scores[i] = nullptr; p.ids[i] = nullptr; p.out_scores[i] = nullptr; p.out_ids[i] = nullptr; p.truncated[i] = nullptr; }
+    for (int i = 0; i < 16; ++i) p.status[i] = (status && i < n_lists) ? status[i] : nullptr;
+    p.redo = status ? redo : nullptr;
     const size_t smem = ((size_t)n_lists * k_in + (size_t)k_out) * 12;
     CUDA_TRY(cudaFuncSetAttribute(drt::merge_sorted_peers_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (8192 + 4096) * 12));
+    if (q_count == 0) {       // nothing to merge on this rank, but it still has to agree on `redo`
+        drt::or_status_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, n_lists);
+        CUDA_TRY(cudaGetLastError());
+        return DRT_OK;
+    }
     drt::merge_sorted_peers_kernel<<<(unsigned)q_count, 256, smem, (cudaStream_t)stream>>>(p, n_lists, (long long)q_begin, k_in, k_out);
     CUDA_TRY(cudaGetLastError());
     return DRT_OK;

@@ -498,6 +498,12 @@ __global__ void f32_to_bf16_kernel(const float4* __restrict__ in, uint2* __restr
     }
 }
 
+// drt_search_async: "this result is not final" (candidate overflow, or the certificate flagged a
+// query) as ONE device byte, so that the caller's merge step — not the host — can look at it.
+__global__ void publish_status_kernel(const int* overflow, const unsigned long long* flagged, unsigned char* status) {
+    if (threadIdx.x == 0) *status = (*overflow != 0 || *flagged != 0ull) ? 1 : 0;
+}
+
 __global__ void fill_outputs_kernel(float* scores, long long* ids, size_t n) {
     for (size_t i = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; i < n;
          i += static_cast<size_t>(gridDim.x) * blockDim.x) {
@@ -642,11 +648,19 @@ struct PeerPtrs {
     float* out_scores[16];
     long long* out_ids[16];
     unsigned char* truncated[16];
+    const unsigned char* status[16];   // per-rank "local result not final" bytes (NULL: not used)
+    unsigned char* redo;               // this rank's OR of all of them
 };
 
 __global__ void __launch_bounds__(256)
 merge_sorted_peers_kernel(PeerPtrs p, int G, long long q_begin, int k_in, int k_out) {
     extern __shared__ uint64_t s_raw[];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.redo) {
+        // every rank reads the same G bytes (written before the first barrier): all ranks agree
+        unsigned char any = 0;
+        for (int g = 0; g < G; ++g) if (p.status[g]) any |= *p.status[g];
+        *p.redo = any;
+    }
     const long long q = q_begin + blockIdx.x;
     const int n = G * k_in;
     long long* s_id = reinterpret_cast<long long*>(s_raw);
@@ -702,6 +716,14 @@ merge_sorted_peers_kernel(PeerPtrs p, int G, long long q_begin, int k_in, int k_
             for (int i = threadIdx.x; i < k_out; i += blockDim.x) { os[i] = s_osc[i]; oi[i] = s_oid[i]; }
         }
         if (threadIdx.x == 0) p.truncated[g][q] = tr;
+    }
+}
+
+__global__ void or_status_kernel(PeerPtrs p, int G) {
+    if (threadIdx.x == 0 && p.redo) {
+        unsigned char any = 0;
+        for (int g = 0; g < G; ++g) if (p.status[g]) any |= *p.status[g];
+        *p.redo = any;
     }
 }
 

@@ -100,9 +100,12 @@ class IndexFlatIP:
                                            _lib.current_stream_ptr(self._device)), "add")
 
     # ---- search -----------------------------------------------------------------------------
-    def search(self, x, k: int, *, id_offset: int = 0, flags: int = 0, out=None):
+    def search(self, x, k: int, *, id_offset: int = 0, flags: int = 0, out=None, status=None):
         """`out=(D, I)`: preallocated contiguous CUDA tensors [nq,k] float32 / int64 the results
-        are written into (device queries only; used by the peer-memory exchange of store.py)."""
+        are written into (device queries only; used by the peer-memory exchange of store.py).
+        `status`: a 1-element CUDA uint8 tensor -> the search runs without any host round trip
+        (`drt_search_async`) and sets status[0] = 1 when its result is not final and the caller
+        must search again without `status` (candidate overflow / a query the certificate flagged)."""
         k = int(k)
         if k <= 0:
             raise RuntimeError(f"search: k must be positive, got {k}")
@@ -124,6 +127,12 @@ class IndexFlatIP:
             else:
                 D = torch.empty((nq, k), dtype=torch.float32, device=x.device)
                 I = torch.empty((nq, k), dtype=torch.int64, device=x.device)
+            if status is not None:
+                with _nvtx("drt.search_async"):
+                    _lib.check(self._lib.drt_search_async(self._h, x.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(),
+                                                          int(id_offset), int(flags), status.data_ptr(),
+                                                          _lib.current_stream_ptr(self._device)), "search_async")
+                return D, I
             with _nvtx("drt.search"):
                 _lib.check(self._lib.drt_search(self._h, x.data_ptr(), nq, k, D.data_ptr(), I.data_ptr(), 1,
                                                 int(id_offset), int(flags),

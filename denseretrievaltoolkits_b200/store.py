@@ -93,7 +93,7 @@ class _PeerExchange:
     @staticmethod
     def _layout(Q: int, kl: int, k: int):
         al = lambda n: (n + 255) // 256 * 256
-        sizes = [Q * kl * 4, Q * kl * 8, Q * k * 4, Q * k * 8, Q]
+        sizes = [Q * kl * 4, Q * kl * 8, Q * k * 4, Q * k * 8, Q, 512]      # last: status byte (peers read it) | redo byte
         offs, o = [], 0
         for n in sizes:
             offs.append(o)
@@ -117,6 +117,7 @@ class _PeerExchange:
         oD = b[offs[2]:offs[2] + Q * k * 4].view(torch.float32).view(Q, k)
         oI = b[offs[3]:offs[3] + Q * k * 8].view(torch.int64).view(Q, k)
         bad = b[offs[4]:offs[4] + Q]
+        self.status, self.redo = b[offs[5]:offs[5] + 1], b[offs[5] + 256:offs[5] + 257]
         return (cD, cI, oD, oI, bad), offs
 
     def my_slice(self, Q: int):
@@ -124,9 +125,10 @@ class _PeerExchange:
         q0 = min(self.rank * per, Q)
         return q0, max(0, min(per, Q - q0))
 
-    def merge(self, offs, Q: int, kl: int, k: int, local_only: bool = False):
+    def merge(self, offs, Q: int, kl: int, k: int, local_only: bool = False, with_status: bool = False):
         """Barrier, merge my query slice from the peers' lists into everyone's result (or, with
-        `local_only`, into mine alone — the flags still go to every rank), barrier."""
+        `local_only`, into mine alone — the flags still go to every rank), barrier.
+        `with_status`: the kernel also ORs every rank's "local result not final" byte into `redo`."""
         import ctypes
 
         lib = _lib.load()
@@ -138,11 +140,13 @@ class _PeerExchange:
             arr = lambda off: (ctypes.c_void_p * W)(*[b + off for b in bases])
             out = (lambda off: (ctypes.c_void_p * W)(*[(b + off) if (not local_only or g == self.rank) else None
                                                         for g, b in enumerate(bases)]))
-            tabs = self._ptr_cache[key] = (arr(offs[0]), arr(offs[1]), out(offs[2]), out(offs[3]), arr(offs[4]))
+            tabs = self._ptr_cache[key] = (arr(offs[0]), arr(offs[1]), out(offs[2]), out(offs[3]), arr(offs[4]), arr(offs[5]),
+                                           bases[self.rank] + offs[5] + 256)
         q0, qn = self.my_slice(Q)
         self.hdl.barrier(channel=0)
-        _lib.check(lib.drt_merge_topk_peers(W, tabs[0], tabs[1], q0, qn, kl, k, tabs[2], tabs[3], tabs[4],
-                                            self.device.index, _lib.current_stream_ptr(self.device.index)),
+        _lib.check(lib.drt_merge_topk_peers2(W, tabs[0], tabs[1], q0, qn, kl, k, tabs[2], tabs[3], tabs[4],
+                                             tabs[5] if with_status else None, tabs[6] if with_status else None,
+                                             self.device.index, _lib.current_stream_ptr(self.device.index)),
                    "merge_topk_peers")
         self.hdl.barrier(channel=0)
 
@@ -311,22 +315,35 @@ class ShardedCorpusStore:
         kl = self.local_depth(k)
         local = bool(local_results) and self.distributed and self.world > 1
         q0, qn = self.result_slice(Q) if local else (0, Q)
-        Dm, Im, bad, owned = self._search_merged(qd, k, kl, flags, local)
-        self.last_search = {"local_depth": kl, "requeried": 0}
+        Dm, Im, bad, owned, redo = self._search_merged(qd, k, kl, flags, local)
+        self.last_search = {"local_depth": kl, "requeried": 0, "redone": 0}
         to_host = host_in and on_gpu
         host = None
+        # the ONE host round trip of a search: re-query count (+ the redo word of the asynchronous
+        # shard searches), and with the host API the result rows in the same transfer
+        nb = bad.sum(dtype=torch.int64).reshape(1) if bad is not None else None
+        if redo is not None:
+            nb = torch.cat([nb if nb is not None else torch.zeros(1, dtype=torch.int64, device=redo.device), redo.to(torch.int64)])
         if to_host:
-            # host API: the result rows and the re-query count travel together, ONE sync
-            nb = bad.sum(dtype=torch.int64).reshape(1) if bad is not None else torch.zeros(1, dtype=torch.int64, device=Dm.device)
+            if nb is None:
+                nb = torch.zeros(1, dtype=torch.int64, device=Dm.device)
             host = _to_host(dev, Dm[q0:q0 + qn], Im[q0:q0 + qn], nb)
-            nbad = int(host[2][0])
+            words = host[2].tolist()
         else:
-            nbad = int(bad.sum().item()) if bad is not None else 0   # same value on every rank (computed from exchanged data)
+            words = nb.tolist() if nb is not None else [0]   # same values on every rank (computed from exchanged data)
+        if redo is not None and words[-1]:
+            # some rank's first pass was not final (candidate overflow / flagged query): all ranks
+            # repeat the step on the synchronous path, which retries and refines
+            Dm, Im, bad, owned, _ = self._search_merged(qd, k, kl, flags, local, allow_async=False)
+            words = [int(bad.sum().item()) if bad is not None else 0]
+            host = None
+            self.last_search["redone"] = 1
+        nbad = int(words[0])
         if nbad:
             idx = bad.nonzero().squeeze(1)
             qt = torch.from_numpy(qd) if isinstance(qd, np.ndarray) else qd
             qb = qt.index_select(0, idx.to(qt.device))
-            Db, Ib, _, _ = self._search_merged(qb.numpy() if isinstance(qd, np.ndarray) else qb, k, k, flags, False)
+            Db, Ib, _, _, _ = self._search_merged(qb.numpy() if isinstance(qd, np.ndarray) else qb, k, k, flags, False, allow_async=False)
             if not owned:
                 Dm, Im = Dm.clone(), Im.clone()
             Dm[idx] = Db
@@ -373,17 +390,24 @@ class ShardedCorpusStore:
                     self._peer = peer
         return self._peer is not False and self.world * kl <= 8192 and k <= 4096 and k <= self.world * kl
 
-    def _search_merged(self, q, k: int, kl: int, flags: int, local: bool = False):
+    def _search_merged(self, q, k: int, kl: int, flags: int, local: bool = False, allow_async: bool = True):
         """Depth-kl search of every shard, candidate exchange, merge to depth k.
-        Returns torch (D [Q,k], I [Q,k], truncated-mask [Q] or None when kl == k, owned) —
+        Returns torch (D [Q,k], I [Q,k], truncated-mask [Q] or None when kl == k, owned, redo) —
         `owned` False: D / I are views of the peer-exchange result region, valid until the next
-        search; with `local` only this rank's `result_slice` rows of D / I are filled."""
+        search; with `local` only this rank's `result_slice` rows of D / I are filled; `redo`
+        (1-element uint8 tensor or None): set when a rank's asynchronous shard search was not
+        final and the step has to be repeated with `allow_async=False`."""
         if self.distributed and self._peer_ok(q, kl, k):
             (cD, cI, oD, oI, bad), offs = self._peer.views(q.shape[0], kl, k)
-            self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags, out=(cD, cI))
+            # shard search without a host round trip when the shape allows it: the search, the
+            # barriers and the merge kernel are then enqueued back to back
+            use_async = (allow_async and q.shape[0] <= 16384 and self.d % 64 == 0 and q.is_contiguous()
+                         and q.dtype is torch.float32 and q.data_ptr() % 16 == 0 and self.shards[0].ntotal > 0)
+            self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags, out=(cD, cI),
+                                  status=self._peer.status if use_async else None)
             with _nvtx("drt.exchange_merge_peers"):
-                self._peer.merge(offs, q.shape[0], kl, k, local_only=local)
-            return oD, oI, (bad.bool() if kl < k else None), False
+                self._peer.merge(offs, q.shape[0], kl, k, local_only=local, with_status=use_async)
+            return oD, oI, (bad.bool() if kl < k else None), False, (self._peer.redo if use_async else None)
         if self.distributed:
             D, I = self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], flags=flags)
             if isinstance(D, np.ndarray):
@@ -391,7 +415,7 @@ class ShardedCorpusStore:
                 if dist.get_backend(self.group) == "nccl":
                     D, I = D.cuda(self.shards[0].device), I.cuda(self.shards[0].device)
             with _nvtx("drt.exchange_merge_nccl"):
-                return self._exchange_and_merge(D, I, k, check=kl < k) + (True,)
+                return self._exchange_and_merge(D, I, k, check=kl < k) + (True, None)
         parts = [s.search(q, kl, id_offset=self._offsets[g], flags=flags) for g, s in enumerate(self.shards)]
         if isinstance(parts[0][0], np.ndarray):
             dev = getattr(self.shards[0], "device", None)
@@ -399,7 +423,34 @@ class ShardedCorpusStore:
             parts = [(to_t(d), to_t(i)) for d, i in parts]
         S = torch.stack([p[0] for p in parts])
         Dm, Im = self._merge(S, torch.stack([p[1] for p in parts]), k)
-        return Dm, Im, (self._truncated(S, Dm, k) if kl < k else None), True
+        return Dm, Im, (self._truncated(S, Dm, k) if kl < k else None), True, None
+
+    def profile_phases(self, q, k: int, reps: int = 5):
+        """Measurement helper (bench.py): CUDA-event times of the two phases of a peer-exchange
+        search on THIS rank — the local shard search, and barrier + exchange/merge kernel +
+        barrier — in ms, averaged over `reps`.  The second includes the wait for the slowest
+        rank (rank skew shows up there).  Returns None when the peer path is not in use."""
+        kl = self.local_depth(k)
+        if not (self.distributed and self._peer_ok(q, kl, k)):
+            return None
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        t_local = t_merge = 0.0
+        for _ in range(reps):
+            (cD, cI, oD, oI, bad), offs = self._peer.views(q.shape[0], kl, k)
+            dist.barrier(group=self.group)
+            ev[0].record()
+            self.shards[0].search(q, kl, id_offset=self._offsets[self.rank], out=(cD, cI))
+            ev[1].record()
+            self._peer.merge(offs, q.shape[0], kl, k)
+            ev[2].record()
+            torch.cuda.synchronize()
+            t_local += ev[0].elapsed_time(ev[1])
+            t_merge += ev[1].elapsed_time(ev[2])
+        W, Q = self.world, q.shape[0]
+        return {"local_search_ms": t_local / reps, "exchange_merge_ms": t_merge / reps,
+                # bytes this rank's merge kernel moves over NVLink: it reads the lists of its Q/W
+                # queries from the W-1 peers and writes the merged rows + flags to the W-1 peers
+                "nvlink_bytes_read": (Q // W) * (W - 1) * kl * 12, "nvlink_bytes_written": (Q // W) * (W - 1) * (k * 12 + 1)}
 
     # candidate entries per rank above which the exchange switches from all-gather (every rank
     # merges all Q queries) to all-to-all (every rank merges Q/W queries, then the merged

@@ -103,6 +103,18 @@ int drt_search(drt_store* s, const float* q, int64_t nq, int k,
                float* out_scores, int64_t* out_ids,
                int io_on_device, int64_t id_offset, uint32_t flags, void* stream);
 
+/* The same search with NO host round trip: device pointers only, fully stream-ordered, the first
+ * pass only.  Instead of retrying / refining on the host, the call publishes ONE device byte:
+ * *status_out = 1 when the result is not final — a candidate buffer overflowed, or the exactness
+ * certificate flagged a query — and the caller must then repeat the search with drt_search.
+ * Made for the multi-GPU path (store.py): the shard search, the exchange + merge kernel and the
+ * barriers are enqueued back to back, the merge kernel ORs all ranks' status bytes
+ * (drt_merge_topk_peers2), and the host reads one word at the end of the step.
+ * 1 <= nq <= 16384, dim a multiple of 64, q 16-byte aligned, non-empty store. */
+int drt_search_async(drt_store* s, const float* q, int64_t nq, int k,
+                     float* out_scores, int64_t* out_ids, int64_t id_offset, uint32_t flags,
+                     uint8_t* status_out, void* stream);
+
 /* Counters of the last drt_search on this store (for tests and bench.py):
  *  [0] kernel launches  [1] mma-filter launches  [2] candidate-buffer overflow retries
  *  [3] first-pass candidates per query (k')      [4] queries whose exactness check flagged
@@ -190,6 +202,15 @@ int drt_inbatch_ce_bwd(const float* x, const float* y, int64_t B, int64_t P, int
 int drt_filter_negatives(const int64_t* ids, int64_t nq, int k, const int64_t* pos_begin,
                          const int64_t* pos_end, int num_negative, int64_t* out_ids,
                          int device, void* stream);
+
+/* drt_merge_topk_peers plus the status exchange of drt_search_async: `status` = one device byte
+ * per rank (peer-mapped), `redo` = this rank's byte that receives their OR (same value on every
+ * rank, since every rank reads the same bytes between the two barriers). */
+int drt_merge_topk_peers2(int n_lists, const float* const* scores, const int64_t* const* ids,
+                          int64_t q_begin, int64_t q_count, int k_in, int k_out,
+                          float* const* out_scores, int64_t* const* out_ids,
+                          uint8_t* const* truncated, const uint8_t* const* status, uint8_t* redo,
+                          int device, void* stream);
 
 #ifdef __cplusplus
 }

@@ -87,6 +87,25 @@ try:
     Dl, Il = peer.search_local_queries(q[rank * per:(rank + 1) * per].contiguous(), 100)
     res["peer_local_queries"] = bool(torch.equal(Il, If[rank * per:(rank + 1) * per]))
     ok = ok and res["peer_local_queries"]
+    res["peer_async_clean"] = peer.last_search.get("redone") == 0       # the asynchronous shard search was final
+    ok = ok and res["peer_async_clean"]
+    # a corpus of near-duplicates (integer rows differing by sparse +1s): the bf16 first pass cannot
+    # be certified, the asynchronous shard searches publish "not final", every rank sees the OR of
+    # the status bytes and the step is repeated on the synchronous path (retry / refine / fp32 pass)
+    gi = torch.Generator(device=dev).manual_seed(9)
+    base = torch.randint(256, 768, (d,), generator=gi, device=dev).float()
+    xi = base[None, :] + (torch.rand(40_000, d, generator=gi, device=dev) < 0.05).float()
+    qi = torch.randint(0, 3, (64, d), generator=gi, device=dev).float()
+    fulli = faiss_compat.IndexFlatIP(d, device=lr, seg_rows=1 << 14)
+    fulli.add(xi)
+    peeri = ShardedCorpusStore(d, device=lr, seg_rows=1 << 14)
+    bi = np.linspace(0, 40_000, world + 1).astype(int)
+    peeri.add(xi[bi[rank]:bi[rank + 1]])
+    peeri.finalize()
+    Dfi, Ifi = fulli.search(qi, 50)
+    Dpi, Ipi = peeri.search(qi, 50)
+    res["peer_redo_path"] = bool(torch.equal(Ipi, Ifi) and torch.equal(Dpi, Dfi)) and peeri.last_search.get("redone") == 1
+    ok = ok and res["peer_redo_path"]
 
     def timeit(st, reps=30):
         for _ in range(5):
