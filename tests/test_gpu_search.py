@@ -324,9 +324,9 @@ def test_reduced_shard_depth_requeries_when_rows_correlate_with_queries():
     D, I = st.search(q, 100)
     np.testing.assert_array_equal(I, Is)
     np.testing.assert_array_equal(D, Ds)
-    assert st.last_search == {"local_depth": 40, "requeried": 64}
+    assert st.last_search == {"local_depth": 40, "requeried": 64, "redone": 0}
     D, I = st.search(torch.from_numpy(q).cuda(), 100)          # now at full depth, device tensors
-    assert st.last_search == {"local_depth": 100, "requeried": 0}
+    assert st.last_search == {"local_depth": 100, "requeried": 0, "redone": 0}
     np.testing.assert_array_equal(I.cpu().numpy(), Is)
     # a few queries only: mixed result rows
     x2 = rng.standard_normal((40000, 256), dtype=np.float32)
