@@ -88,6 +88,19 @@ try:
     res["peer_local_queries"] = bool(torch.equal(Il, If[rank * per:(rank + 1) * per]))
     ok = ok and res["peer_local_queries"]
     res["peer_async_clean"] = peer.last_search.get("redone") == 0       # the asynchronous shard search was final
+    # Trainer.evaluate with queries batched across loader steps (collective DeferredSearch): every
+    # rank queues its OWN 16-query batches, one corpus pass per 128 queued queries per rank
+    from denseretrievaltoolkits_b200.deferred import DeferredSearch
+    mine = q[rank * per:(rank + 1) * per]
+    steps = [mine[i:i + 16].contiguous() for i in range(0, min(320, per // 16 * 16), 16)]
+    ds = DeferredSearch(peer, 100, max_queries=128)
+    got = list(ds.results(enumerate(steps)))
+    same = len(got) == len(steps) and ds.searches == -(-len(steps) * 16 // 128)
+    for (tag, (Dd, Id)), st_ in zip(got, steps):
+        lo = rank * per + tag * 16
+        same = same and bool(torch.equal(Id, If[lo:lo + 16]) and torch.equal(Dd, Df[lo:lo + 16]))
+    res["peer_deferred_evaluate"] = same
+    ok = ok and same
     ok = ok and res["peer_async_clean"]
     # a corpus of near-duplicates (integer rows differing by sparse +1s): the bf16 first pass cannot
     # be certified, the asynchronous shard searches publish "not final", every rank sees the OR of
