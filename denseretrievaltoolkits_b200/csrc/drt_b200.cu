@@ -153,6 +153,7 @@ struct drt_store {
     int dim = 0;          // row pitch in elements: the caller's dim rounded up to a multiple of 64, zero padded
     int dim_user = 0;     // the caller's embedding dim (rows / queries / reconstruct use this pitch)
     int split = 0;        // dims [split, dim) are the caller-declared exactly-representable tail (default: none)
+    int f16 = 0;          // 16-bit planes are bf16 (default) or IEEE fp16 (DRT_B200_FIRST_PASS=f16), fixed at creation
     int device = 0;
     int64_t seg_rows = 0;
     int64_t ntotal = 0;
@@ -196,8 +197,21 @@ namespace {
 // rho = E / sigma_tail is ~0.4 for 768-d Gaussian-like embeddings at N ~ 1e7 (E ~ 2.5 at score
 // scale 27.7: 2 |q| |d| 2^-8 / sqrt(6) + accumulation); k' is the smallest count with
 // ln(k'/k) >= rho + 4 sqrt((k'-k)/(k k')).  `scale` widens rho for stores whose searches flagged.
-int kprime_for(int k, double scale = 1.0) {
-    static const double rho0 = [] { const char* e = getenv("DRT_B200_KPRIME_RHO"); return e ? atof(e) : 0.40; }();
+bool first_pass_f16_default() {
+    // bf16 by default: fp16 images give an 8x tighter certificate (k' 140 instead of 200 at k=100)
+    // but the wider multipliers draw more power, and under the 1000 W cap the tensor-bound pass ran
+    // 4.6 % slower (SM clock 1.22 vs 1.29 GHz, same box, profiles/r2_results.md) — a net loss at
+    // large Q.  DRT_B200_FIRST_PASS=f16 selects fp16 (a gain for HBM-bound small-Q calls).
+    static const bool f16 = [] { const char* e = getenv("DRT_B200_FIRST_PASS"); return e && !strcmp(e, "f16"); }();
+    return f16;
+}
+
+int kprime_for(int k, double scale = 1.0, int f16 = -1) {
+    static const double rho_env = [] { const char* e = getenv("DRT_B200_KPRIME_RHO"); return e ? atof(e) : -1.0; }();
+    if (f16 < 0) f16 = first_pass_f16_default() ? 1 : 0;
+    // E / sigma_tail for 768-d Gaussian-like data: ~0.4 with bf16 images (E ~ 2.6 at score scale
+    // 27.7), ~0.07 with fp16 images (E ~ 0.45); fp16 keeps a wider safety factor for real data
+    const double rho0 = rho_env >= 0.0 ? rho_env : (f16 ? 0.12 : 0.40);
     const double rho = rho0 * scale;
     int kp = k + std::max(28, k / 5);
     for (; kp < 8192; kp += 4) {
@@ -379,7 +393,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                  int64_t id_offset, uint32_t flags, cudaStream_t st, int attempt, int kctas,
                  int keep_override, unsigned char* qflag, int64_t* flagged_out) {
     const int dim = s->dim;
-    const int keep = keep_override > 0 ? keep_override : kprime_for(k, s->margin_scale);
+    const int keep = keep_override > 0 ? keep_override : kprime_for(k, s->margin_scale, s->f16);
     const int sel = select_capacity(keep);
     const int cap = kCandCap;
     if (cap < 2 * keep) return fail(DRT_E_UNSUPPORTED, "k=%d too large for the candidate buffer", k);
@@ -412,6 +426,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     CUDA_TRY(cudaMemcpyAsync(s->tile_table.p, s->seg_tile.data(), s->seg_tile.size() * sizeof(float4*),
                              cudaMemcpyHostToDevice, st));
     const bool exact_pass = (kctas == 0);    // fp32 SIMT first pass (last-resort refinement)
+    const int q_f16 = s->f16;
     const float4* qbound = (const float4*)s->qbound.p;
     const float4* const* bound_table = (const float4* const*)s->bound_table.p;
     const float4* const* tile_table = (const float4* const*)s->tile_table.p;
@@ -439,7 +454,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         const float c_k2 = (float)(dim / 128 + 8) * 0x1p-23f;
         const int blocks = (int)std::min<int64_t>((nq + 7) / 8, (int64_t)s->sm_count * 8);
         drt::prep_queries_kernel<<<blocks, 256, 0, st>>>(q_dev, (int)nq, dim, s->split, exact_pass ? nullptr : (uint2*)s->q_bf16.p,
-                                                        (float4*)s->qbound.p, thr, cnt, c_acc, c_k2, exact_pass ? 1 : 0);
+                                                        (float4*)s->qbound.p, thr, cnt, c_acc, c_k2, exact_pass ? 1 : 0, q_f16);
         s->stats[0] += 1;
     }
     CUtensorMap tmap_q;
@@ -501,6 +516,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
             p.unit_tiles /= 2;
         p.num_k_blocks = dim / drt::kBlockK;
         p.nq = (int)nq;
+        p.f16 = s->f16;
         p.rows_valid = (uint32_t)c.row1;    // rows past this chunk's end are not admitted yet
         p.row_base = (uint32_t)((int64_t)c.seg * s->seg_rows);
         p.cap = (uint32_t)cap;
@@ -546,7 +562,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
                                                        (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
                                                        (long long)id_offset, out_s, (long long*)out_i,
                                                        (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag,
-                                                       exact_pass ? 0 : 1, thr);
+                                                       exact_pass ? 0 : 1, thr, qbound);
         s->stats[0] += 1;
     }
     CUDA_TRY(cudaGetLastError());
@@ -599,7 +615,7 @@ int search_retrying(drt_store* s, const float* q_dev, int64_t nq, int k, float* 
 // (up to 3 rounds); what is still flagged afterwards is reported in stats[4].
 int refine_flagged(drt_store* s, const float* q_dev, int64_t nq, int k, float* out_s, int64_t* out_i,
                    int64_t id_offset, uint32_t flags, cudaStream_t st, unsigned char* qflag, int64_t* flagged) {
-    int keep = kprime_for(k, s->margin_scale);
+    int keep = kprime_for(k, s->margin_scale, s->f16);
     std::vector<unsigned char> hflag;
     std::vector<int> idx;
     for (int round = 0; *flagged > 0 && round < 3 && keep * 2 <= 8192; ++round) {
@@ -704,6 +720,7 @@ int drt_store_create(drt_store** out, int dim, int device, int64_t seg_rows) {
     drt_store* s = new (std::nothrow) drt_store();
     if (!s) return fail(DRT_E_OOM, "host allocation failed");
     s->dim = dim_pad; s->dim_user = dim; s->split = dim_pad; s->device = device; s->seg_rows = seg_rows;
+    s->f16 = first_pass_f16_default() ? 1 : 0;
     cudaDeviceGetAttribute(&s->sm_count, cudaDevAttrMultiProcessorCount, device);
     if (cudaHostAlloc((void**)&s->err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
         cudaHostGetDevicePointer((void**)&s->err_dev, s->err_host, 0) != cudaSuccess ||
@@ -761,7 +778,7 @@ int drt_store_add(drt_store* s, const float* rows, int64_t n, int rows_on_device
         const int blocks = (int)std::min<int64_t>((take + 7) / 8, (int64_t)s->sm_count * 16);
         drt::ingest_rows_kernel<<<blocks, 256, 0, st>>>(dst, (long long)take, s->dim, s->split,
                                                        (uint2*)((char*)sg.bf16 + (size_t)off * row_bf16), sg.bound, sg.tile,
-                                                       (long long)off);
+                                                       (long long)off, s->f16);
         CUDA_TRY(cudaGetLastError());
         s->ntotal += take;
         s->heavy_valid = false;

@@ -49,6 +49,7 @@ struct FilterParams {
     int unit_tiles;         // corpus tiles per work unit
     int num_k_blocks;       // dim / 64
     int nq;
+    int f16;                // the 16-bit planes (queries and corpus) are IEEE fp16, not bf16
     uint32_t rows_valid;    // rows of this segment that may be admitted by this launch
     uint32_t row_base;      // store row id of the segment's first row
     uint32_t cap;           // candidate slots per query
@@ -75,9 +76,15 @@ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
 }
 
 // ---- exactness certificate: a rigorous bound on |first-pass score - fp32 rescoring score| -----
-// Row j stores rb = (r, Dx, Dt): r = |d - bf16(d)|_2 over all dims, Dx = |d[0:split)|_2,
+// Row j stores rb = (r, Dx, Dt): r = |d - image(d)|_2 over all dims, Dx = |d[0:split)|_2,
 // Dt = |d[split:)|_2 (split = dim unless the caller declares an exactly-representable tail);
-// query q carries qb = (A, B, C) = (|q~|(1+c_acc), e_x + c, e_t + c) with q~ = bf16(q),
+// query q carries qb = (A, B, C) = (|q~|(1+c_acc), e_x + c, e_t + c) with q~ = the 16-bit image of q
+// the tensor core sees: bf16 by default, IEEE fp16 on both sides with DRT_B200_FIRST_PASS=f16 (three
+// more significand bits: the rounding terms shrink 8x, but the MMA draws more power — see
+// drt_b200.cu).  fp16's narrow range costs nothing in rigour: r is the EXACT residual norm of whatever image was stored (row
+// values beyond +-65504 saturate and simply get a large r), and a query whose magnitudes fall
+// outside [2^-6, 2^14] is scaled by a power of two sigma (kept in qb.w) that scales that
+// query's whole first-pass domain: s~, ub, thr,
 // e_x / e_t = |q - q~|_2 over the head / tail dims and c = c_acc |q~| + c_32 |q| covering the
 // tensor core's fp32 accumulation (worst case: operands aligned to the largest exponent and
 // TRUNCATED, 18 ulp of the running magnitude per K=16 step) and the rounding of the fp32
@@ -270,7 +277,7 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
     } else if (warp == 1) {
         // ================================ MMA issuer ==================================
         if (rank == 0 && ptx::elect_one()) {
-            const uint32_t idesc = ptx::make_idesc_bf16(kTileM * kCtas, kTileN);
+            const uint32_t idesc = p.f16 ? ptx::make_idesc_f16(kTileM * kCtas, kTileN) : ptx::make_idesc_bf16(kTileM * kCtas, kTileN);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;

@@ -214,6 +214,11 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
 __host__ __device__ constexpr uint32_t make_idesc_bf16(uint32_t M, uint32_t N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
 }
+// Same with both operands in IEEE fp16 (format code 0).  kind::f16 wants A and B in the SAME 16-bit
+// format: fp16 x bf16 raises an illegal-instruction fault on sm_100a (tried, round 2).
+__host__ __device__ constexpr uint32_t make_idesc_f16(uint32_t M, uint32_t N) {
+    return (1u << 4) | (0u << 7) | (0u << 10) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
 
 }  // namespace ptx
 }  // namespace drt

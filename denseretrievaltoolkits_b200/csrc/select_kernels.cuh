@@ -6,6 +6,7 @@
 // tensor cores.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cfloat>
 #include "inbatch_ce.cuh"
 #include "mips_filter.cuh"
@@ -35,40 +36,76 @@ __device__ __forceinline__ void bitonic_sort_desc_u64(uint64_t* keys, int P) {
     __syncthreads();
 }
 
-// Query preparation, one warp per query: fp32 -> bf16 (round to nearest even) for the tensor-core
-// pass, the query's error-bound coefficients qb = (A, B, C) (mips_filter.cuh), and the initial
-// search state (threshold -FLT_MAX like faiss' heap, empty candidate list).
+// Query preparation, one warp per query: fp32 -> the 16-bit image the tensor core reads, the
+// query's error-bound coefficients qb = (A, B, C, sigma) (mips_filter.cuh), and the initial search
+// state (threshold -FLT_MAX like faiss' heap, empty candidate list).
+//   f16 = 1: image = fp16(sigma q) (round to nearest even), sigma a power of two that brings
+//     max|q_i| to ~1 when it lies outside [2^-6, 2^14] (fp16 overflows at 65504 and loses
+//     precision below 6e-5), else 1.  The query's first-pass scores, upper bounds and threshold
+//     all live in the sigma-scaled domain; K2 multiplies exact scores by sigma to compare.
+//   f16 = 0: image = bf16(q), sigma = 1.
 //   exact_mode = 1 (fp32 SIMT first pass of the last-resort refinement): A = B = C = 0, rows are
 //   selected by their fp32 scores as they are (exact ties keep the canonical id order).
+__device__ __forceinline__ float image16(float x, int f16) {
+    return f16 ? __half2float(__float2half_rn(x)) : __bfloat162float(__float2bfloat16_rn(x));
+}
+// row values: fp16 saturates at +-65504 instead of overflowing to inf (the residual norm then
+// carries the difference, so the bound stays valid and the row is simply always a candidate)
+__device__ __forceinline__ float sat16(float x, int f16) {
+    return (f16 && x == x) ? fminf(fmaxf(x, -65504.f), 65504.f) : x;
+}
+
 __global__ void __launch_bounds__(256)
-prep_queries_kernel(const float* __restrict__ q, int nq, int dim, int split, uint2* __restrict__ q_bf16,
+prep_queries_kernel(const float* __restrict__ q, int nq, int dim, int split, uint2* __restrict__ q16,
                     float4* __restrict__ qbound, float* __restrict__ thr, uint32_t* __restrict__ cnt,
-                    float c_acc, float c_32, int exact_mode) {
+                    float c_acc, float c_32, int exact_mode, int f16) {
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
     const float up = 1.f + 0x1p-10f;      // covers the rounding of the fp32 sums / sqrt below
     for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < nq; i += warps) {
         const float4* src = reinterpret_cast<const float4*>(q + static_cast<size_t>(i) * dim);
-        uint2* dst = q_bf16 ? q_bf16 + static_cast<size_t>(i) * (dim >> 2) : nullptr;
+        uint2* dst = q16 ? q16 + static_cast<size_t>(i) * (dim >> 2) : nullptr;
+        float sigma = 1.f;
+        if (f16 && !exact_mode) {
+            float mx = 0.f;
+            for (int j = lane; j < (dim >> 2); j += 32) {
+                const float4 v = src[j];
+                mx = fmaxf(mx, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (mx > 0.f && mx < 3.0e38f && (mx >= 16384.f || mx < 0x1p-6f)) {
+                int e;
+                frexpf(mx, &e);                       // mx = m 2^e, m in [0.5, 1)
+                sigma = ldexpf(1.f, -e);              // sigma mx in [0.5, 1)
+            }
+        }
         float s_t = 0.f, s_ex = 0.f, s_et = 0.f, s_n = 0.f;
         for (int j = lane; j < (dim >> 2); j += 32) {
             const float4 v = src[j];
-            const float x[4] = {v.x, v.y, v.z, v.w};
+            const float x[4] = {v.x * sigma, v.y * sigma, v.z * sigma, v.w * sigma};     // exact: power of two
             float xt[4];
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                xt[c] = __bfloat162float(__float2bfloat16_rn(x[c]));
+                xt[c] = image16(x[c], f16);
                 const float e = x[c] - xt[c];                  // exact in fp32
                 s_t = fmaf(xt[c], xt[c], s_t);
                 s_n = fmaf(x[c], x[c], s_n);
                 if (4 * j + c < split) s_ex = fmaf(e, e, s_ex); else s_et = fmaf(e, e, s_et);
             }
             if (dst) {
-                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-                const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
                 uint2 o;
-                o.x = *reinterpret_cast<const uint32_t*>(&lo);
-                o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                if (f16) {
+                    const __half2 lo = __floats2half2_rn(x[0], x[1]);
+                    const __half2 hi = __floats2half2_rn(x[2], x[3]);
+                    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                } else {
+                    const __nv_bfloat162 lo = __floats2bfloat162_rn(x[0], x[1]);
+                    const __nv_bfloat162 hi = __floats2bfloat162_rn(x[2], x[3]);
+                    o.x = *reinterpret_cast<const uint32_t*>(&lo);
+                    o.y = *reinterpret_cast<const uint32_t*>(&hi);
+                }
                 dst[j] = o;
             }
         }
@@ -93,7 +130,7 @@ prep_queries_kernel(const float* __restrict__ q, int nq, int dim, int split, uin
             if (!(A < kBoundHuge)) A = kBoundHuge;             // also catches NaN
             if (!(B < kBoundHuge)) B = kBoundHuge;
             if (!(C < kBoundHuge)) C = kBoundHuge;
-            qbound[i] = make_float4(A, B, C, 0.f);
+            qbound[i] = make_float4(A, B, C, sigma);
             thr[i] = -FLT_MAX;                                  // faiss: heap starts at -FLT_MAX
             cnt[i] = 0u;
         }
@@ -302,7 +339,7 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
                const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
                int k, long long id_offset, float* out_scores, long long* out_ids,
                int do_rescore, unsigned long long* flagged, unsigned char* qflag, int check,
-               const float* __restrict__ thr) {
+               const float* __restrict__ thr, const float4* __restrict__ qbound) {
     extern __shared__ uint64_t s_keys[];            // [P] then dim floats
     __shared__ unsigned int s_taulb;                // min exact score of the best-k-by-ub (ordered encoding)
     __shared__ unsigned int s_done;                 // rows actually rescored (statistics)
@@ -312,6 +349,7 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
     float* s_q = reinterpret_cast<float*>(s_keys + next_pow2_dev(static_cast<int>(keep)));
     for (int j = threadIdx.x; j < dim; j += blockDim.x) s_q[j] = q_f32[static_cast<size_t>(q) * dim + j];
     if (threadIdx.x == 0) { s_taulb = 0xFFFFFFFFu; s_done = 0u; }
+    const float sigma = qbound[q].w;    // the first-pass domain (ub, thr) of this query is scaled by sigma (a power of two)
 
     const uint64_t* row = cand + static_cast<size_t>(q) * cap;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -338,7 +376,7 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
                 if (lane == 0) {
                     const bool ok = acc > -FLT_MAX;    // also false for NaN
                     s_keys[i] = ok ? pack_key(acc, r) : 0ull;
-                    if (pass == 0) atomicMin(&s_taulb, ok ? float_to_ordered(acc) : 0u);
+                    if (pass == 0) atomicMin(&s_taulb, ok ? float_to_ordered(acc * sigma) : 0u);
                     atomicAdd(&s_done, 1u);
                 }
             }
@@ -369,7 +407,7 @@ rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t
             const float bound = thr[q];
             if (bound > -FLT_MAX) {
                 const bool have_k = n >= k && s_keys[k - 1] != 0ull;
-                flag = !have_k || !(ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32)) > bound);
+                flag = !have_k || !(ordered_to_float(static_cast<uint32_t>(s_keys[k - 1] >> 32)) * sigma > bound);
             }
         }
         if (flag) atomicAdd(flagged, 1ull);
@@ -438,7 +476,7 @@ exact_filter_kernel(const float* __restrict__ q, long long nq, const float* __re
 // per element, 16 B per row.
 __global__ void __launch_bounds__(256)
 ingest_rows_kernel(const float* __restrict__ plane, long long n, int dim, int split, uint2* __restrict__ bf16,
-                   float4* __restrict__ row_bound, unsigned int* __restrict__ tile_bound, long long row0) {
+                   float4* __restrict__ row_bound, unsigned int* __restrict__ tile_bound, long long row0, int f16) {
     const int lane = threadIdx.x & 31;
     const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
     const float up = 1.f + 0x1p-10f;
@@ -451,15 +489,22 @@ ingest_rows_kernel(const float* __restrict__ plane, long long n, int dim, int sp
             const float x[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
-                const float e = x[c] - __bfloat162float(__float2bfloat16_rn(x[c]));   // exact in fp32
+                const float e = x[c] - image16(sat16(x[c], f16), f16);                // exact in fp32 (inf when x is)
                 s_r = fmaf(e, e, s_r);
                 if (4 * j + c < split) s_x = fmaf(x[c], x[c], s_x); else s_t = fmaf(x[c], x[c], s_t);
             }
-            const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
-            const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
             uint2 o;
-            o.x = *reinterpret_cast<const uint32_t*>(&lo);
-            o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            if (f16) {
+                const __half2 lo = __floats2half2_rn(sat16(v.x, 1), sat16(v.y, 1));
+                const __half2 hi = __floats2half2_rn(sat16(v.z, 1), sat16(v.w, 1));
+                o.x = *reinterpret_cast<const uint32_t*>(&lo);
+                o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            } else {
+                const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y);
+                const __nv_bfloat162 hi = __floats2bfloat162_rn(v.z, v.w);
+                o.x = *reinterpret_cast<const uint32_t*>(&lo);
+                o.y = *reinterpret_cast<const uint32_t*>(&hi);
+            }
             dst[j] = o;
         }
 #pragma unroll

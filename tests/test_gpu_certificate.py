@@ -39,24 +39,55 @@ def _assert_lists_equal_up_to_fp32_ties(D, I, Dr, Ir, x, q):
         assert diff.mean() < 0.002
 
 
-def test_planted_high_norm_row_whose_bf16_score_falls_below_the_candidates():
+def test_planted_high_norm_rows_whose_first_pass_score_falls_below_the_candidates():
+    """Two planted rows, each the exact top-1 of one query, each built so that 16-bit rounding —
+    bf16 for row A / query 0, fp16 for row B / query 1 — removes ~600 from its first-pass score
+    (see oracle/bound.py::adverse_row).  Whichever format the library's first pass uses, one of
+    them has a NEGATIVE first-pass score, far below the ~k' best first-pass scores (> 80): an error
+    estimate taken from the candidates (max ~0.2; round 1's check) would never look at it."""
     rng = np.random.default_rng(21)
     n, d, nq, k = 100_000, 768, 64, 10
     x = rng.standard_normal((n, d), dtype=np.float32)
     q = rng.standard_normal((nq, d), dtype=np.float32)
-    x[54_321] = bound.adverse_row(q[0])
-    # premise: exact top-1 of query 0, but its first-pass (bf16) score is negative, i.e. far
-    # below the ~k' best first-pass scores (> 80): an error estimate taken from the candidates
-    # (max ~0.2) would never look at it
-    assert float(q[0].astype(np.float64) @ x[54_321].astype(np.float64)) > 250.0
-    assert float(bound.first_pass_scores(x[54_321:54_322], q[:1])[0, 0]) < 0.0
+    ia, ib = 54_321, 12_345
+    x[ia] = bound.adverse_row(q[0], 256.0, "bf16")
+    x[ib] = bound.adverse_row(q[1], 2048.0, "f16")
+    for qi, row, fmt in ((0, ia, "bf16"), (1, ib, "f16")):
+        assert float(q[qi].astype(np.float64) @ x[row].astype(np.float64)) > 250.0
+        assert float(bound.first_pass_scores(x[row:row + 1], q[qi:qi + 1], fmt)[0, 0]) < 0.0
     index = _mk(seg_rows=1 << 15)
     index.add(x)
     D, I = index.search(q, k)
     st = index.search_stats()
     Dr, Ir = _exact_f64(x, q, k)
-    assert I[0, 0] == 54_321, "the planted row must be found: exactness is a proof, not an estimate"
+    # (row A has norm ~7,000, so it can also outrank row B for query 1: B is rank 1 or 2 there)
+    assert Ir[0, 0] == ia and ib in Ir[1, :2]
+    assert I[0, 0] == ia and ib in I[1, :2], "the planted rows must be found: exactness is a proof, not an estimate"
     _assert_lists_equal_up_to_fp32_ties(D, I, Dr, Ir, x, q)
+    assert st["flagged_queries"] == 0
+
+
+def test_values_beyond_the_fp16_range_and_tiny_queries():
+    """fp16 images saturate at +-65504 and flush below 6e-8: rows with huge components, queries
+    with huge or tiny magnitudes (scaled by a power of two), all still exact."""
+    rng = np.random.default_rng(26)
+    n, d, nq, k = 60_000, 768, 48, 20
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    x[100] *= 1e6                                    # every component beyond the fp16 range
+    x[200, 5] = 3e5
+    x[300, 7] = -2e5
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    q[3] *= 1e6
+    q[4] *= 1e-9
+    q[5] *= 40000.0
+    index = _mk(seg_rows=1 << 14)
+    index.add(x)
+    D, I = index.search(q, k)
+    st = index.search_stats()
+    Dr, Ir = _exact_f64(x, q, k)
+    np.testing.assert_allclose(D, Dr, rtol=3e-5, atol=0)
+    diff = I != Ir
+    assert diff.mean() < 0.005 and np.all(np.abs(D[diff] - Dr[diff]) <= 3e-5 * np.abs(Dr[diff]))
     assert st["flagged_queries"] == 0
 
 
@@ -141,3 +172,19 @@ def test_small_index_allocates_a_small_segment():
     D, I = idx[0].search(q, 10)
     Dr, Ir = _exact_f64(allx, q, 10)
     np.testing.assert_array_equal(I, Ir)
+
+
+def test_fp16_first_pass_mode_in_a_subprocess():
+    """DRT_B200_FIRST_PASS=f16 (fp16 images on both sides: 8x tighter bound, k' 140 instead of 200)
+    is read once per process, so the adversarial and range cases are re-run in a child process."""
+    import os
+    import subprocess
+    import sys
+
+    env = dict(os.environ, DRT_B200_FIRST_PASS="f16")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    p = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_certificate.py"), "-q", "-m", "gpu", "-x",
+                        "-k", "planted or beyond_the_fp16 or huge_rows or statistics"], env=env, capture_output=True, text=True,
+                       timeout=900, cwd=root)
+    assert p.returncode == 0, p.stdout[-3000:] + p.stderr[-2000:]
+    assert "4 passed" in p.stdout, p.stdout[-500:]
