@@ -335,6 +335,13 @@ def main():
     torch.cuda.synchronize()
     build_s = time.perf_counter() - t_build0
     q_dev = make_queries(torch, nq, device)
+    shard_rows = None
+    if store is not None and os.environ.get("DRT_B200_REBALANCE", "0") == "1":
+        # optional (off by default: measured at N=2 the per-GPU speed differences under the power cap
+        # drift between the calibration and the run, 35.50 -> 35.36 ms per step, within noise):
+        # rows per rank proportional to the measured speed of the rank's GPU; global row ids unchanged
+        shard_rows = store.rebalance(q_dev, k)
+        row0, row1 = store._offsets[rank], store._offsets[rank + 1]
     q_host = torch.empty((nq, DIM), dtype=torch.float32).pin_memory()
     q_host.copy_(q_dev)
     q_np = q_host.numpy()
@@ -475,7 +482,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": HEADLINE["name"] if (nq, n, k) == (HEADLINE["nq"], HEADLINE["n"], HEADLINE["k"])
                        else f"custom: {nq} queries x {n}x{DIM}, k={k}",
-                       "nq": nq, "n": n, "dim": DIM, "k": k, "sharding": f"rows/{world}",
+                       "nq": nq, "n": n, "dim": DIM, "k": k,
+                       "sharding": f"rows/{world}" + ("" if not shard_rows else f", contiguous shards sized by measured GPU speed: {shard_rows}"),
                        "shard_depth": store.last_search.get("local_depth") if store is not None else k,
                        "exchange": (None if store is None else
                                     "one kernel over peer-mapped memory (drt_merge_topk_peers)" if store._peer not in (None, False)

@@ -171,6 +171,18 @@ class IndexFlatIP:
     def reconstruct(self, i: int) -> np.ndarray:
         return self.reconstruct_n(int(i), 1)[0]
 
+    def reconstruct_n_device(self, i0: int = 0, n: int | None = None):
+        """`reconstruct_n` into a CUDA tensor on the store's device (no host round trip)."""
+        import torch
+
+        if n is None:
+            n = self.ntotal - i0
+        out = torch.empty((int(n), self.d), dtype=torch.float32, device=torch.device("cuda", self._device))
+        if n:
+            _lib.check(self._lib.drt_store_reconstruct(self._h, int(i0), int(n), out.data_ptr(), 1,
+                                                       _lib.current_stream_ptr(self._device)), "reconstruct_n_device")
+        return out
+
 
 def _default_device() -> int:
     try:

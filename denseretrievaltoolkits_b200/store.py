@@ -225,6 +225,90 @@ class ShardedCorpusStore:
             self.finalize()
         return self._offsets[-1]
 
+    def rebalance(self, q_probe, k: int = 100, reps: int = 5, max_shift: float = 0.10, granularity: int = 256):
+        """Speed-proportional row split (collective, NCCL groups).
+
+        The ranks' GPUs do not run at the same clock under the power cap (measured: 3-5 % between
+        the fastest and the slowest shard search of one step), and a step ends when the slowest
+        rank does.  This measures every rank's shard-search time for `q_probe`, moves the shard
+        boundaries so that rows per rank are proportional to the measured speed (by at most
+        `max_shift` of a shard, in multiples of `granularity` rows), and ships the boundary rows to
+        the neighbouring ranks with one all-to-all.  Global row ids do not change: shards stay
+        contiguous ranges of the same global order, only `finalize()`'s offsets move.
+        Returns the new per-rank row counts."""
+        if not (self.distributed and self.world > 1 and dist.get_backend(self.group) == "nccl"):
+            return [s.ntotal for s in self.shards]
+        if self._offsets is None:
+            self.finalize()
+        shard = self.shards[0]
+        dev = torch.device("cuda", shard.device)
+        W, r, d = self.world, self.rank, self.d
+        old = list(self._offsets)
+        total = old[-1]
+        kl = self.local_depth(k)
+        times = []
+        for i in range(reps + 2):
+            dist.barrier(group=self.group)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            shard.search(q_probe, kl, id_offset=old[r])
+            e1.record()
+            torch.cuda.synchronize(dev)
+            if i >= 2:
+                times.append(e0.elapsed_time(e1))
+        t = torch.tensor([sorted(times)[len(times) // 2]], dtype=torch.float64, device=dev)
+        ts = [torch.zeros_like(t) for _ in range(W)]
+        dist.all_gather(ts, t, group=self.group)
+        ts = [float(x.item()) for x in ts]
+        counts = [old[g + 1] - old[g] for g in range(W)]
+        if min(ts) <= 0 or min(counts) == 0:
+            return counts
+        rate = [counts[g] / ts[g] for g in range(W)]
+        want = [total * rate[g] / sum(rate) for g in range(W)]
+        new_counts = []
+        for g in range(W):
+            lo, hi = counts[g] * (1.0 - max_shift), counts[g] * (1.0 + max_shift)
+            new_counts.append(int(min(max(want[g], lo), hi)) // granularity * granularity)
+        new_counts[-1] += total - sum(new_counts)              # the last shard takes the rounding remainder
+        if min(new_counts) <= 0:
+            return counts
+        new = shard_offsets(new_counts)
+        # rows of mine that go to rank j: [old_r, old_r+1) ∩ [new_j, new_j+1)
+        def overlap(a0, a1, b0, b1):
+            lo, hi = max(a0, b0), min(a1, b1)
+            return (lo, hi) if hi > lo else (lo, lo)
+        send = [overlap(old[r], old[r + 1], new[j], new[j + 1]) for j in range(W)]
+        recv = [overlap(old[j], old[j + 1], new[r], new[r + 1]) for j in range(W)]
+        send_rows = [hi - lo for lo, hi in send]
+        recv_rows = [hi - lo for lo, hi in recv]
+        keep_lo, keep_hi = send[r]
+        kept = shard.reconstruct_n_device(keep_lo - old[r], keep_hi - keep_lo)
+        send_rows[r] = recv_rows[r] = 0                          # my own rows do not travel
+        outbuf = torch.cat([shard.reconstruct_n_device(send[j][0] - old[r], send_rows[j]) for j in range(W)], dim=0) \
+            if sum(send_rows) else torch.empty((0, d), dtype=torch.float32, device=dev)
+        inbuf = torch.empty((sum(recv_rows), d), dtype=torch.float32, device=dev)
+        dist.all_to_all_single(inbuf, outbuf, output_split_sizes=recv_rows, input_split_sizes=send_rows, group=self.group)
+        pieces, pos = [], 0
+        for j in range(W):                                       # ascending source rank = ascending global row id
+            if j == r:
+                pieces.append(kept)
+            elif recv_rows[j]:
+                pieces.append(inbuf[pos:pos + recv_rows[j]])
+                pos += recv_rows[j]
+        torch.cuda.synchronize(dev)
+        shard.reset()
+        for p in pieces:
+            for r0 in range(0, p.shape[0], 1 << 20):
+                shard.add(p[r0:r0 + (1 << 20)])
+        torch.cuda.synchronize(dev)
+        del kept, outbuf, inbuf, pieces
+        self._offsets = None
+        offs = self.finalize()
+        if offs != new:
+            raise RuntimeError(f"rebalance: shard sizes {offs} do not match the plan {new}")
+        self.last_rebalance = {"search_ms": ts, "rows_before": counts, "rows_after": new_counts}
+        return new_counts
+
     # ---- persistence ------------------------------------------------------------------------
     def save(self, directory: str) -> None:
         """Every rank writes its own shard as a faiss IndexFlat file (`shard{g}.faiss`, readable

@@ -102,6 +102,14 @@ try:
     res["peer_deferred_evaluate"] = same
     ok = ok and same
     ok = ok and res["peer_async_clean"]
+    # speed-proportional re-split of the shards: rows move between neighbouring ranks, global ids do not
+    before = list(peer._offsets)
+    new_counts = peer.rebalance(q, 100, reps=3, max_shift=0.25)
+    Df, If = full.search(q, 100)
+    Dp, Ip = peer.search(q, 100)
+    res["peer_rebalance"] = bool(torch.equal(Ip, If) and torch.equal(Dp, Df)) and sum(new_counts) == n and peer._offsets[-1] == n
+    res["rebalance_rows"] = [before, list(peer._offsets)]
+    ok = ok and res["peer_rebalance"]
     # a corpus of near-duplicates (integer rows differing by sparse +1s): the bf16 first pass cannot
     # be certified, the asynchronous shard searches publish "not final", every rank sees the OR of
     # the status bytes and the step is repeated on the synchronous path (retry / refine / fp32 pass)
