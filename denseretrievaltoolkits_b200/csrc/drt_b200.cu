@@ -108,6 +108,22 @@ int make_tmap_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t d
     return DRT_OK;
 }
 
+// fp32 row-major [rows, dim] matrix, box = [64 k-elements x box_rows rows], no swizzle (the fused
+// loss kernel converts it to bf16 pieces itself)
+int make_tmap_f32(CUtensorMap* map, const void* base, uint64_t rows, uint64_t dim, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) return fail(DRT_E_CUDA, "cuTensorMapEncodeTiled entry point not available");
+    cuuint64_t gdim[2] = {dim, rows};
+    cuuint64_t gstride[1] = {dim * 4};
+    cuuint32_t box[2] = {64, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), gdim, gstride, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(DRT_E_CUDA, "cuTensorMapEncodeTiled (fp32) failed: CUresult %d", (int)r);
+    return DRT_OK;
+}
+
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
@@ -1156,6 +1172,7 @@ int ce_tc_setup(CeWorkspace& w, cudaStream_t st) {
         CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_nt_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::GemmTcCfg<2>::kSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_small_kernel<drt::kStore>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::kSmallSmemBytes));
         CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_small_kernel<drt::kCe>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::kSmallSmemBytes));
+        CUDA_TRY(cudaFuncSetAttribute(drt::gemm_tc_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)drt::kFusedSmemBytes));
         if (cudaHostAlloc((void**)&w.err_host, sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
             cudaHostGetDevicePointer((void**)&w.err_dev, w.err_host, 0) != cudaSuccess) {
             (void)cudaGetLastError();
@@ -1278,6 +1295,52 @@ int drt_inbatch_ce_fwd(const float* x, const float* y, int64_t B, int64_t P, int
     CeWorkspace& w = g_ce_ws[std::make_pair(device, stream)];
     const int path = ce_path(B, P, dim);
     const long long* tg = (const long long*)target;
+    static const bool no_fuse = getenv("DRT_B200_CE_NOFUSE") != nullptr;
+    if (path == kPathSmall && B <= drt::kTileM && dim % 64 == 0 && aligned16(x) && aligned16(y) && !no_fuse) {
+        // ONE launch: the kernel reads the fp32 operands, splits them into bf16 pieces in shared
+        // memory, contracts, reduces the K-chunks and finishes the cross entropy.  Only with a
+        // single row tile (B <= 128, the reference's per-GPU batches): every y tile is then
+        // converted exactly once; with more row tiles the conversion work would be repeated per
+        // row tile and the separate preparation launch is cheaper (measured at 256 x 2048)
+        if ((rc = ce_tc_setup(w, st)) != DRT_OK) return rc;
+        drt::SmallParams sp = {};
+        drt::SmallProblem& pb = sp.prob[0];
+        pb.m_tiles = (int)((B + drt::kTileM - 1) / drt::kTileM);
+        pb.n_tiles = (int)((P + drt::kSmallTileN - 1) / drt::kSmallTileN);
+        pb.num_k_blocks = dim / 64;                    // SOURCE k-blocks: each becomes 6 piece products
+        const int tiles = pb.m_tiles * pb.n_tiles;
+        if (tiles > kTicketSlots - 64) return fail(DRT_E_UNSUPPORTED, "loss shape needs %d tiles on the small-tile path", tiles);
+        static const int max_split = [] { const char* e = getenv("DRT_B200_CE_KSPLIT_MAX"); return e ? std::max(1, atoi(e)) : 32; }();
+        // K-chunks of EQUAL length (a divisor of the k-block count): the tile's finisher waits for its
+        // slowest chunk, so 9 chunks of 1-2 k-blocks were slower than 6 chunks of 2
+        const int limit = std::max(1, std::min(std::min(148 / std::max(1, tiles), pb.num_k_blocks), max_split));
+        pb.ksplit = 1;
+        for (int dv = 1; dv <= limit; ++dv) if (pb.num_k_blocks % dv == 0) pb.ksplit = dv;
+        pb.M = B; pb.N = P; pb.C = logits_out;
+        unsigned int* tickets = (unsigned int*)w.ticket.p;
+        pb.tile_ticket = tickets + 64;
+        pb.partials = nullptr;
+        if (pb.ksplit > 1) {
+            if ((rc = w.partials.ensure((size_t)tiles * pb.ksplit * drt::kTileM * drt::kSmallTileN * 4)) != DRT_OK) return rc;
+            pb.partials = (float*)w.partials.p;
+        }
+        if ((rc = w.part_max.ensure((size_t)B * pb.n_tiles * 4)) != DRT_OK) return rc;
+        if ((rc = w.part_sum.ensure((size_t)B * pb.n_tiles * 4)) != DRT_OK) return rc;
+        if ((rc = w.tgt.ensure((size_t)B * 4)) != DRT_OK) return rc;
+        CUtensorMap tx, ty;
+        if ((rc = make_tmap_f32(&tx, x, (uint64_t)B, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
+        if ((rc = make_tmap_f32(&ty, y, (uint64_t)P, (uint64_t)dim, drt::kSmallTileN)) != DRT_OK) return rc;
+        sp.prob[1] = sp.prob[0];
+        sp.ctas0 = tiles * pb.ksplit;
+        sp.err = w.err_dev;
+        sp.ce.target = tg; sp.ce.target_stride = P / B; sp.ce.loss_scale = loss_scale;
+        sp.ce.part_max = (float*)w.part_max.p; sp.ce.part_sum = (float*)w.part_sum.p; sp.ce.tgt_logit = (float*)w.tgt.p;
+        sp.ce.ticket = tickets; sp.ce.lse_out = lse_out; sp.ce.loss_rows = loss_rows; sp.ce.loss_out = loss_out;
+        if (const char* e = getenv("DRT_B200_CE_TRACE")) sp.dbg = (unsigned long long*)strtoull(e, nullptr, 0);   // dev: device buffer address
+        drt::gemm_tc_fused_kernel<<<sp.ctas0, drt::kSmallThreads, drt::kFusedSmemBytes, st>>>(tx, ty, sp);
+        CUDA_TRY(cudaGetLastError());
+        return DRT_OK;
+    }
     if (path == kPathSmall) {
         // one launch prepares both operands (exact bf16x3 split), one launch does the contraction,
         // the split-K reduction and the cross entropy; logits are stored only when asked for
