@@ -348,7 +348,9 @@ def main():
 
     def step_device():
         if store is not None:
-            return store.search(q_dev, k, flags=flags)    # local shard search + exchange + merge
+            # shard search + exchange + merge; every rank keeps the merged rows of its own slice of
+            # the queries on its device (rank-local results, as in the e2e leg)
+            return store.search(q_dev, k, flags=flags, local_results=True)
         return index.search(q_dev, k, flags=flags)
 
     def step_host():
@@ -397,7 +399,7 @@ def main():
     e2e_value = nq * args.steps / (ms_e2e / 1e3)
 
     # ---- parity, outside the timed region: the (merged) result against an independent search ----
-    Dm, Im = step_device()
+    Dm, Im = store.search(q_dev, k, flags=flags) if store is not None else step_device()     # full result on every rank
     last = dict(store.last_search) if store is not None else {}
     st_now = index.search_stats()
     cert = torch.tensor([st_now["flagged_queries"], st_now["exact_queries"], st_now["refined_queries"]],
@@ -483,6 +485,7 @@ def main():
             "config": {"workload": HEADLINE["name"] if (nq, n, k) == (HEADLINE["nq"], HEADLINE["n"], HEADLINE["k"])
                        else f"custom: {nq} queries x {n}x{DIM}, k={k}",
                        "nq": nq, "n": n, "dim": DIM, "k": k,
+                       "results": "every rank keeps the merged rows of its slice of the queries" if store is not None else "one device",
                        "sharding": f"rows/{world}" + ("" if not shard_rows else f", contiguous shards sized by measured GPU speed: {shard_rows}"),
                        "shard_depth": store.last_search.get("local_depth") if store is not None else k,
                        "exchange": (None if store is None else
