@@ -1,16 +1,12 @@
-// inbatch_ce.cuh — K4/K5: in-batch-negative score matrix + cross entropy, forward and backward.
+// inbatch_ce.cuh — the fp32 SIMT form of K4/K5: in-batch-negative score matrix + cross entropy,
+// forward and backward, for the shapes the tensor-core kernels do not take (a contraction length
+// that is not a multiple of 4: the split operand's row pitch must be 16-byte aligned), and the
+// register-tiled SIMT GEMM core that the last-resort exact search pass (exact_filter_kernel)
+// shares.  The reference's own shapes run on tcgen05: gemm_tc_small.cuh / gemm_tc.cuh.
 //
 // Replaces `logits = x @ y.T; F.cross_entropy(logits, target)` of SimpleContrastiveLoss.forward
 // (DRT/trainer/losses.py:16-17) and the loss block of DRModel.forward
 // (DRT/model/biencoder.py:107-116), plus their autograd.
-//
-// The reference computes this in fp32 (TF32 is off by default for torch.matmul), and the loss
-// must match to 1e-4 relative, so the contraction runs as fp32 FFMA (a single bf16 tensor-core
-// pass would put ~5e-4 relative error on the loss).  At the named shape (128 x 1024 x 768,
-// 0.2 GFLOP, 3.5 MB of operands) the step is launch-latency bound, not FLOP bound; the win
-// over the eager path is one launch for scores + log-sum-exp + NLL + reduction, and three
-// launches for the backward (elementwise dlogits from the kept logits, dx, dy).  Large shapes
-// (B*P*d >= 2e9) take the tcgen05 path in gemm_tc.cuh instead.
 //
 // One register-tiled SIMT GEMM core serves all three contractions:
 //   NT  logits  = x · yᵀ          A(m,k)=x[m*d+k]    B(k,n)=y[n*d+k]

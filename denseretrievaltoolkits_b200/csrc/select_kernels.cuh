@@ -1,6 +1,8 @@
-// select_kernels.cuh — the integer/index side of the search path: candidate-list trimming and
-// threshold publication (between corpus chunks), exact fp32 rescoring + final ordering, the
-// fp32->bf16 ingest conversion, the cross-shard merge and the mining filter.
+// select_kernels.cuh — the integer/index side of the search path: query preparation (16-bit image
+// + error-bound coefficients), candidate-list trimming by upper bound and threshold publication
+// (between corpus chunks), exact fp32 rescoring + final ordering + the exactness certificate, the
+// ingest kernel (16-bit plane + per-row / per-tile error-bound tables), the cross-shard merge
+// (incl. the peer-memory exchange form) and the mining filter.
 //
 // These are HBM/L2-bound byte and index kernels: coalesced loads, shared-memory staging, no
 // tensor cores.

@@ -1,9 +1,11 @@
 """Mirror of the contrastive losses in `DRT/trainer/losses.py` on fused B200 kernels.
 
 `SimpleContrastiveLoss.forward(x, y, target=None, reduction='mean')` (losses.py:11-17) and
-`DistributedContrastiveLoss` (losses.py:20-40) keep their names, arguments and values; the
-score matrix, log-sum-exp, NLL and the reduction run as ONE CUDA launch (`drt_inbatch_ce_fwd`)
-and the backward as three (`drt_inbatch_ce_bwd`), all fp32 like the reference's `torch.matmul`.
+`DistributedContrastiveLoss` (losses.py:20-40) keep their names, arguments and values.  At the
+reference's per-GPU shapes (B <= 128) the score matrix, log-sum-exp, NLL and the reduction run as
+ONE CUDA launch on the tensor cores (`drt_inbatch_ce_fwd`; two launches with more row tiles) and
+the backward as two (`drt_inbatch_ce_bwd`), fp32-accurate like the reference's `torch.matmul`
+(exact 3-way bf16 split).  The backward never writes a saved tensor.
 `inbatch_scores_and_loss` serves the loss block of `DRModel.forward`
 (DRT/model/biencoder.py:107-119), which also returns the score matrix (biencoder.py:122).
 

@@ -3,10 +3,11 @@
 Replaces the reference's corpus hand-off — per-rank `.npy` + id JSONL, rank-0 `index.add` of
 every shard, `faiss.write_index`, `faiss.read_index` on every other rank, then each rank
 searching a full CPU replica (`DRT/trainer/trainer.py:191-262,287-297`) — with: every rank keeps
-the rows it encoded on its own GPU, a search runs the local shard on each GPU, the per-shard
-top-k candidate lists ([Q,k] fp32 scores + int64 global ids) are exchanged with one NCCL
-all-gather over NVLink, and a merge kernel (`drt_merge_topk`, the device form of
-`merge_retrieval_results_by_score`, `DRT/model/utils.py:215-229`) produces the global top-k.
+the rows it encoded on its own GPU, a search runs the local shard on each GPU (without a host
+round trip: `drt_search_async`), and the per-shard top-k candidate lists ([Q,k_l] fp32 scores +
+int64 global ids) are exchanged and merged by ONE kernel over peer-mapped memory
+(`drt_merge_topk_peers2`; NCCL all-gather / all-to-all + `drt_merge_topk` as the alternative) —
+the device form of `merge_retrieval_results_by_score`, `DRT/model/utils.py:215-229`.
 
 Global ids follow the reference's concatenation order: rank-major, insertion order inside a
 rank (rank 0's rows first, trainer.py:225-241 iterates the per-rank files and appends).
