@@ -152,6 +152,24 @@ class _PeerExchange:
         self.hdl.barrier(channel=0)
 
 
+def plan_rebalance(counts, times, max_shift: float = 0.10, granularity: int = 256):
+    """Row counts proportional to the measured speed counts[g] / times[g] of every shard, each
+    moved by at most `max_shift` of its current size, in multiples of `granularity` (the last
+    shard takes the rounding remainder).  Returns the old counts when the plan is degenerate."""
+    counts = [int(c) for c in counts]
+    total = sum(counts)
+    if not counts or min(counts) <= 0 or min(times) <= 0:
+        return counts
+    rate = [c / t for c, t in zip(counts, times)]
+    want = [total * r / sum(rate) for r in rate]
+    new = []
+    for c, w in zip(counts, want):
+        lo, hi = c * (1.0 - max_shift), c * (1.0 + max_shift)
+        new.append(int(min(max(w, lo), hi)) // granularity * granularity)
+    new[-1] += total - sum(new)
+    return new if min(new) > 0 else counts
+
+
 def shard_offsets(counts) -> list[int]:
     """Global id of each shard's first row, rank-major (exclusive prefix sum) + total."""
     off = [0]
@@ -262,16 +280,8 @@ class ShardedCorpusStore:
         dist.all_gather(ts, t, group=self.group)
         ts = [float(x.item()) for x in ts]
         counts = [old[g + 1] - old[g] for g in range(W)]
-        if min(ts) <= 0 or min(counts) == 0:
-            return counts
-        rate = [counts[g] / ts[g] for g in range(W)]
-        want = [total * rate[g] / sum(rate) for g in range(W)]
-        new_counts = []
-        for g in range(W):
-            lo, hi = counts[g] * (1.0 - max_shift), counts[g] * (1.0 + max_shift)
-            new_counts.append(int(min(max(want[g], lo), hi)) // granularity * granularity)
-        new_counts[-1] += total - sum(new_counts)              # the last shard takes the rounding remainder
-        if min(new_counts) <= 0:
+        new_counts = plan_rebalance(counts, ts, max_shift, granularity)
+        if new_counts == counts:
             return counts
         new = shard_offsets(new_counts)
         # rows of mine that go to rank j: [old_r, old_r+1) ∩ [new_j, new_j+1)

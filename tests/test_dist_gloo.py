@@ -68,6 +68,8 @@ def _worker(rank, world, port, out_dir):
     Dc, Ic = stc.search(q, 200)
     depthc = dict(stc.last_search)
     Dl, Il = st.search_local_queries(torch.from_numpy(q[rank * 3:(rank + 1) * 3]), 20)
+    Ds, Is = st.search(q, 20, local_results=True)                 # every rank keeps its slice of the queries
+    assert st.result_slice(6) == (rank * 3, 3) and np.array_equal(np.asarray(Is), np.asarray(I)[rank * 3:(rank + 1) * 3])
     t = torch.full((2, 3), float(rank), requires_grad=True)
     g = gather_rank_major(t, rank, world)
     g.sum().backward()
@@ -109,3 +111,18 @@ def test_shard_offsets_rank_major():
     from denseretrievaltoolkits_b200.store import shard_offsets
 
     assert shard_offsets([3, 0, 5]) == [0, 3, 3, 8]
+
+
+def test_rebalance_plan_is_speed_proportional_bounded_and_conserves_rows():
+    from denseretrievaltoolkits_b200.store import plan_rebalance
+
+    counts = [1_100_000] * 8
+    times = [8.0, 8.1, 8.4, 8.0, 8.2, 8.05, 8.3, 8.0]           # ms per shard search
+    new = plan_rebalance(counts, times, max_shift=0.10, granularity=256)
+    assert sum(new) == sum(counts) and all(c % 256 == 0 for c in new[:-1])
+    assert new[2] < new[0] and new[6] < new[3]                     # slower GPUs get fewer rows
+    assert all(abs(n - c) <= 0.10 * c + 256 * 8 for n, c in zip(new, counts))
+    est = [t * n / c for t, n, c in zip(times, new, counts)]
+    assert max(est) - min(est) < 0.02 * max(est)                   # predicted times equalised
+    assert plan_rebalance([10, 0, 5], [1.0, 1.0, 1.0]) == [10, 0, 5]      # degenerate: unchanged
+    assert plan_rebalance([1000, 1000], [1.0, 100.0], max_shift=0.25, granularity=1) == [1250, 750]
