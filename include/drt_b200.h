@@ -124,6 +124,8 @@ int drt_search_async(drt_store* s, const float* q, int64_t nq, int k,
  *  [9] queries whose certificate failed after the FIRST pass (searched again with a larger k';
  *      [4] counts what is still uncertified after the whole ladder)
  *  [10] candidate rows whose fp32 row was actually read by the rescoring kernel   [11] reserved */
+/* After drt_search_async this call waits for that search to finish (its counters are collected
+ * lazily, so that the search itself needs no host round trip). */
 int drt_search_stats(const drt_store* s, int64_t out[12]);
 
 /* Host-side planning, exposed for tests (no device needed).  drt_plan_params: k' (first-pass
