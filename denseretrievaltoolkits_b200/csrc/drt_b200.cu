@@ -426,7 +426,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     if ((rc = s->heavy.ensure(std::max<size_t>(8, s->segs.size()))) != DRT_OK) return rc;
     if ((rc = s->seg_valid.ensure(std::max<size_t>(8, s->segs.size() * 8))) != DRT_OK) return rc;
     if ((rc = s->qbound.ensure((size_t)nq * sizeof(float4))) != DRT_OK) return rc;
-    if ((rc = s->sel_scratch.ensure((size_t)nq * keep * 8)) != DRT_OK) return rc;
+    if ((rc = s->sel_scratch.ensure((size_t)nq * 2 * keep * 8)) != DRT_OK) return rc;
 
     float* thr = (float*)s->thr.p;
     uint32_t* cnt = (uint32_t*)s->cnt.p;
@@ -481,18 +481,22 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     // `expect` = candidates a query is expected to hold at this select.  The shared-memory staging
     // area is sized for ~1.5x that (not for the worst case `sel`): more selecting CTAs fit an SM,
     // and a query that gathered more takes the kernel's global-memory path.
-    auto launch_select = [&](double expect) {
+    auto launch_select = [&](double expect, bool final_select) {
+        // between chunks the select may keep up to 2 k' candidates (it then stops after one digit
+        // pass); the last one before K2 is exact
+        // (and so is every select of the overflow-retry attempts: their chunk sizes count on k' survivors)
+        const uint32_t max_keep = (final_select || attempt > 0) ? (uint32_t)keep : (uint32_t)(2 * keep);
         int keys = 1024;
         while (keys < sel && keys < 1.5 * expect + 256) keys *= 2;
         keys = std::min(keys, sel);
         if (s->any_heavy)
             drt::select_kernel<true><<<(int)nq, 256, (size_t)keys * 12, st>>>(
                 cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow, qbound, bound_table, tile_table,
-                (const unsigned char*)s->heavy.p, (uint32_t)s->seg_rows, (uint32_t)keys, (uint64_t*)s->sel_scratch.p);
+                (const unsigned char*)s->heavy.p, (uint32_t)s->seg_rows, (uint32_t)keys, (uint64_t*)s->sel_scratch.p, max_keep);
         else
             drt::select_kernel<false><<<(int)nq, 256, (size_t)keys * 8, st>>>(
                 cand, cnt, thr, (uint32_t)cap, (uint32_t)keep, overflow, qbound, bound_table, tile_table,
-                (const unsigned char*)s->heavy.p, (uint32_t)s->seg_rows, (uint32_t)keys, (uint64_t*)s->sel_scratch.p);
+                (const unsigned char*)s->heavy.p, (uint32_t)s->seg_rows, (uint32_t)keys, (uint64_t*)s->sel_scratch.p, max_keep);
         s->stats[0] += 1;
     };
     int64_t seen_at_select = 0;      // rows scanned when the thresholds were last refreshed
@@ -510,7 +514,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
             drt::exact_filter_kernel<C><<<grid, C::THREADS, 0, st>>>(
                 q_dev, (long long)nq, rows, (long long)nrows, dim, (uint32_t)((int64_t)c.seg * s->seg_rows + c.row0), thr,
                 cnt, cand, (uint32_t)cap, aligned16_ptr(q_dev) ? 1 : 0, qbound, s->seg_bound[c.seg] + c.row0);
-            launch_select((double)sel);
+            launch_select((double)sel, &c == &chunks.back());
             s->stats[0] += 1;
             continue;
         }
@@ -562,9 +566,10 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
             // candidates held now: all rows of the first chunk; later the k' survivors plus what the
             // rows since the last refresh admitted against that (by now stale) threshold,
             // ~k' (seen - seen_then) / seen_then
+            // (x1.25 + k': an early-stopped select leaves up to 2 k' candidates and a slightly lower threshold)
             const double expect = seen_at_select == 0 ? (double)std::min<int64_t>(seen, cap)
-                                                      : (double)keep * (double)seen / (double)seen_at_select;
-            launch_select(attempt == 0 ? expect : (double)sel);
+                                                      : 1.25 * (double)keep * (double)seen / (double)seen_at_select + keep;
+            launch_select(attempt == 0 ? expect : (double)sel, last);
             seen_at_select = seen;
             // thresholds frozen: the final select must still find its candidates in shared memory
             if (attempt == 0 && (double)keep * (double)(s->ntotal - seen) / (double)seen < (double)(sel - keep) / 2.0) frozen = true;

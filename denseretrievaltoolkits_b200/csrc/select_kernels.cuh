@@ -183,7 +183,11 @@ __global__ void __launch_bounds__(256)
 select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t keep,
               int* overflow, const float4* __restrict__ qbound, const float4* const* __restrict__ seg_bound,
               const float4* const* __restrict__ seg_tile, const unsigned char* __restrict__ seg_heavy,
-              uint32_t seg_rows, uint32_t smem_keys, uint64_t* scratch) {
+              uint32_t seg_rows, uint32_t smem_keys, uint64_t* scratch, uint32_t max_keep) {
+    // max_keep >= keep: the select may stop as soon as a digit boundary leaves between keep and
+    // max_keep candidates (threshold = that boundary, a valid if slightly lower bound; usually
+    // after ONE pass).  Between chunks the list only has to shrink and the threshold to rise; the
+    // final select before K2 passes max_keep = keep and is exact.
     extern __shared__ uint64_t s_keys[];             // [smem_keys] tightened keys, then [smem_keys] stored scores
     uint32_t* s_orig = reinterpret_cast<uint32_t*>(s_keys + smem_keys);
     __shared__ uint32_t s_hist[256];
@@ -263,6 +267,10 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
                 if ((key & mask) == prefix) s_pivot = key;
             }
             found = true;
+        } else if (keep - s_need + s_bucket <= max_keep) {
+            // everything from this digit's lower edge upwards: keep .. max_keep candidates
+            if (tid == 0) s_pivot = prefix;
+            found = true;
         }
         __syncthreads();
         // the next digit may overlap bits already fixed when shift < 8: harmless, the overlapping
@@ -278,16 +286,18 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
         }
     } else {
         // compact through the scratch row (the list cannot be rewritten in place while it is read)
-        uint64_t* tmp = scratch + static_cast<size_t>(q) * keep;
+        uint64_t* tmp = scratch + static_cast<size_t>(q) * max_keep;
         for (uint32_t i = tid; i < n; i += blockDim.x) {
             const uint64_t stored = row[i];
             if (tight(stored) >= pivot) tmp[atomicAdd(&s_out, 1u)] = stored;
         }
         __syncthreads();
-        for (uint32_t i = tid; i < keep; i += blockDim.x) row[i] = tmp[i];
+        const uint32_t kept = s_out;
+        for (uint32_t i = tid; i < kept; i += blockDim.x) row[i] = tmp[i];
     }
+    __syncthreads();
     if (tid == 0) {
-        cnt[q] = keep;
+        cnt[q] = s_out;                   // keep, or up to max_keep after an early stop
         thr[q] = ordered_to_float(static_cast<uint32_t>(pivot >> 32));
     }
 }
