@@ -203,6 +203,7 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
     if (n <= keep) return;
     uint64_t* row = cand + static_cast<size_t>(q) * cap;
     const float4 qb = qbound[q];
+    const uint32_t old_thr_o = float_to_ordered(thr[q]);
     const bool in_smem = n <= smem_keys;
     // the lists keep the STORED (tile-level) keys, so tightening is applied afresh by every select
     auto tight = [&](uint64_t stored) -> uint64_t {
@@ -267,8 +268,11 @@ select_kernel(uint64_t* cand, uint32_t* cnt, float* thr, uint32_t cap, uint32_t 
                 if ((key & mask) == prefix) s_pivot = key;
             }
             found = true;
-        } else if (keep - s_need + s_bucket <= max_keep) {
-            // everything from this digit's lower edge upwards: keep .. max_keep candidates
+        } else if (keep - s_need + s_bucket <= max_keep && static_cast<uint32_t>(prefix >> 32) >= old_thr_o) {
+            // everything from this digit's lower edge upwards: keep .. max_keep candidates.  Only
+            // if that edge does not fall below the threshold already published (the exact
+            // keep-th never does): with a wide score range the first digits are coarse, and a
+            // lowered threshold would flood the next chunk with admissions.
             if (tid == 0) s_pivot = prefix;
             found = true;
         }

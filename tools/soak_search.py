@@ -56,6 +56,8 @@ for it in range(iters):
     st = index.search_stats()
     agg["refined"] += st["refined_queries"]; agg["flagged"] += st["flagged_queries"]; agg["exact"] += st["exact_queries"]
     agg["overflow"] += st["overflow_retries"]
+    if st["overflow_retries"]:
+        agg.setdefault("overflow_cases", []).append((fam, n, d, k, nq, seg_rows))
     s = q.double() @ x.double().t()
     kk = min(k, n)
     Dr, Ir = torch.topk(s, kk, dim=1)
