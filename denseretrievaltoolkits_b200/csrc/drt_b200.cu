@@ -543,6 +543,7 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         p.thr = thr; p.cnt = cnt; p.cand = cand; p.err = s->err_dev;
         p.qbound = qbound;
         p.tile_bound = (const float4*)s->segs[c.seg].tile;
+        p.row_bound = s->segs[c.seg].bound;
         const bool timed = (flags & DRT_SEARCH_TIME_KERNELS) != 0;
         if (timed) {
             while (s->ev.size() < 2 * (n_timed + 1)) {

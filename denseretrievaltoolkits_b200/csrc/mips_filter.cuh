@@ -55,7 +55,8 @@ struct FilterParams {
     uint32_t cap;           // candidate slots per query
     const float* thr;       // [nq] admission threshold on the UPPER-BOUND score (strict >)
     const float4* qbound;   // [nq] per-query error-bound coefficients (A, B, C, -), see below
-    const float4* tile_bound; // this segment's per-256-row-tile maxima of the row bounds (r, Dx, Dt, -)
+    const float4* tile_bound; // this segment's per-256-row-tile maxima of the row bounds (r, Dx, Dt, 1/min|d|)
+    const float4* row_bound;  // this segment's per-row bounds (read only for tiles that mix very different norms)
     uint32_t* cnt;          // [nq] candidates appended so far (may exceed cap: overflow)
     uint64_t* cand;         // [nq][cap] packed (ordered UPPER-BOUND score << 32 | ~row)
     int* err;               // host-mapped watchdog flag
@@ -142,9 +143,15 @@ __device__ __noinline__ void flush_staging(uint32_t my_stage, uint32_t n, const 
 // Filter 32 consecutive scores of one query (registers v) against thr.  `row_id0` is the store
 // row id of v[0]; only the first `nvalid` columns exist in the corpus.
 // A hit is staged with its tile-level upper bound s~ + et (rounded up) as the key's score.
+// `heavy` (warp-uniform): the tile mixes row norms more than 1.5x apart — typically one outlier row
+// whose bound makes et huge, so that EVERY row of the tile passes the tile-level test (200 outliers
+// per 2^20 rows would admit 51k rows per query and overflow the candidate buffers).  Such tiles
+// re-test each hit against the row's own bound (`rb`, a warp-uniform 16-byte load per row).
+template <bool kHeavy>
 __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr, float et, uint32_t row_id0,
                                              int nvalid, uint32_t my_stage, uint32_t& scnt,
-                                             const FilterParams& p, int q) {
+                                             const FilterParams& p, int q, float thr_pub,
+                                             const float4& qb, const float4* rb) {
     // maxima of the four 8-column sub-blocks: the warp only walks a sub-block in which some
     // lane has a hit, so the admission cost stays proportional to the (rare) hits
     float mb[4];
@@ -166,7 +173,8 @@ __device__ __forceinline__ void filter_chunk(const uint32_t (&v)[32], float thr,
 #pragma unroll
                 for (int j = 8 * b; j < 8 * b + 8; ++j) {
                     const float f = __uint_as_float(v[j]);
-                    const bool hit = (f > thr) && (j < nvalid);
+                    bool hit = (f > thr) && (j < nvalid);
+                    if constexpr (kHeavy) hit = hit && (__fadd_ru(f, bound_term(qb, __ldg(rb + j))) > thr_pub);
                     const uint64_t key = pack_key(__fadd_ru(f, et), row_id0 + j);
                     if (hit) asm volatile("st.shared.u64 [%0], %1;" ::"r"(my_stage + scnt * kSlotStride), "l"(key) : "memory");
                     scnt += hit ? 1u : 0u;
@@ -338,19 +346,32 @@ mips_filter_kernel(const __grid_constant__ CUtensorMap tmap_q,
                 ptx::tc_fence_after();
                 const float et = bound_term(qb, tb);
                 const float thr_eff = __fsub_rd(thr, et);
+                const bool heavy = !(tb.y * tb.w <= 1.5f);        // max|d| / min|d| of the tile (NaN / inf: heavy)
 
                 const uint32_t taddr = tmem_base + ((quarter * 32u) << 16) + acc * kTileN + half * kColsPerWarp;
                 const uint32_t col0 = half * kColsPerWarp;
+                const float4* rb_tile = p.row_bound + row0 + col0;
                 uint32_t va[32], vb[32];
                 ptx::tmem_ld_32x32(taddr, va);
+                const uint32_t id0 = p.row_base + row0 + col0;
+                const int nv0 = valid_cols - static_cast<int>(col0);
+                if (!heavy) {
 #pragma unroll 1
-                for (int c = 0; c < kColsPerWarp / 32; c += 2) {
-                    tmem_ld_wait_regs(va);
-                    ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
-                    filter_chunk(va, thr_eff, et, p.row_base + row0 + col0 + c * 32, valid_cols - static_cast<int>(col0) - c * 32, my_stage, scnt, p, qc);
-                    tmem_ld_wait_regs(vb);
-                    if (c + 2 < kColsPerWarp / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
-                    filter_chunk(vb, thr_eff, et, p.row_base + row0 + col0 + (c + 1) * 32, valid_cols - static_cast<int>(col0) - (c + 1) * 32, my_stage, scnt, p, qc);
+                    for (int c = 0; c < kColsPerWarp / 32; c += 2) {
+                        tmem_ld_wait_regs(va);
+                        ptx::tmem_ld_32x32(taddr + (c + 1) * 32, vb);
+                        filter_chunk<false>(va, thr_eff, et, id0 + c * 32, nv0 - c * 32, my_stage, scnt, p, qc, thr, qb, rb_tile);
+                        tmem_ld_wait_regs(vb);
+                        if (c + 2 < kColsPerWarp / 32) ptx::tmem_ld_32x32(taddr + (c + 2) * 32, va);
+                        filter_chunk<false>(vb, thr_eff, et, id0 + (c + 1) * 32, nv0 - (c + 1) * 32, my_stage, scnt, p, qc, thr, qb, rb_tile);
+                    }
+                } else {
+#pragma unroll 1
+                    for (int c = 0; c < kColsPerWarp / 32; ++c) {
+                        tmem_ld_wait_regs(va);
+                        filter_chunk<true>(va, thr_eff, et, id0 + c * 32, nv0 - c * 32, my_stage, scnt, p, qc, thr, qb, rb_tile + c * 32);
+                        if (c + 1 < kColsPerWarp / 32) ptx::tmem_ld_32x32(taddr + (c + 1) * 32, va);
+                    }
                 }
                 // accumulator stage drained: hand it back to the MMA issuer (leader CTA's barrier)
                 ptx::tc_fence_before();

@@ -132,6 +132,27 @@ def test_a_few_huge_rows_do_not_poison_every_query():
     assert st["refined_queries"] <= nq // 4
 
 
+def test_outlier_rows_do_not_flood_the_candidate_buffers():
+    """An outlier row makes its 256-row tile's bound so large that the tile-level test would pass
+    every row of the tile: 120 such tiles in one segment are 30,720 admissions per query, over the
+    16,384-entry candidate buffer (4.4M rows of this family took 601 launches and 57 ms before the
+    filter re-tested rows of mixed-norm tiles against their own bounds; 15 launches / 10.5 ms after)."""
+    rng = np.random.default_rng(29)
+    n, d, nq, k = 160_000, 768, 64, 100
+    x = rng.standard_normal((n, d), dtype=np.float32)
+    big = np.arange(120) * 1280 + 77          # distinct tiles, one segment
+    x[big] *= 1000.0
+    q = rng.standard_normal((nq, d), dtype=np.float32)
+    index = _mk()
+    index.add(x)
+    D, I = index.search(q, k)
+    st = index.search_stats()
+    Dr, Ir = _exact_f64(x, q, k)
+    _assert_lists_equal_up_to_fp32_ties(D, I, Dr, Ir, x, q)
+    assert st["overflow_retries"] == 0, st
+    assert st["flagged_queries"] == 0 and st["exact_queries"] == 0
+
+
 def test_certificate_statistics_on_gaussian_data():
     """The default k' certifies (nearly) every query of the benchmark distribution in one pass."""
     rng = np.random.default_rng(24)
