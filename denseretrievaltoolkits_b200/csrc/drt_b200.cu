@@ -260,7 +260,8 @@ int set_kernel_attrs(drt_store* s) {
                                   (int)drt::FilterCfg<2>::kSmemBytes));
     CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     CUDA_TRY(cudaFuncSetAttribute(drt::select_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // 8192 keys + 8192 dims
+    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));   // 8192 keys + 8192 dims
+    CUDA_TRY(cudaFuncSetAttribute(drt::rescore_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     s->attrs_set = true;
     return DRT_OK;
 }
@@ -580,7 +581,15 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     }
     {
         const size_t smem = (size_t)next_pow2(keep) * 8 + (size_t)dim * 4;
-        drt::rescore_kernel<<<(int)nq, 256, smem, st>>>(cand, cnt, (uint32_t)cap, (uint32_t)keep, q_dev, dim,
+        // few queries: one CTA of 32 warps per query (latency-bound gathers); many: 8 warps, 6 CTAs per SM
+        if (nq <= 2 * (int64_t)s->sm_count)
+            drt::rescore_kernel<1024><<<(int)nq, 1024, smem, st>>>(cand, cnt, (uint32_t)cap, (uint32_t)keep, q_dev, dim,
+                                                       (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
+                                                       (long long)id_offset, out_s, (long long*)out_i,
+                                                       (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag,
+                                                       exact_pass ? 0 : 1, thr, qbound);
+        else
+            drt::rescore_kernel<256><<<(int)nq, 256, smem, st>>>(cand, cnt, (uint32_t)cap, (uint32_t)keep, q_dev, dim,
                                                        (const float* const*)s->seg_table.p, (uint32_t)s->seg_rows, k,
                                                        (long long)id_offset, out_s, (long long*)out_i,
                                                        (flags & DRT_SEARCH_NO_RESCORE) ? 0 : 1, flagged, qflag,

@@ -350,7 +350,11 @@ __device__ __forceinline__ float rescore_dot(const float4* __restrict__ x4, cons
     return acc;
 }
 
-__global__ void __launch_bounds__(256, 6)
+// kThreads: 256 (six CTAs per SM when there are thousands of queries) or 1024 for small batches
+// (at most two queries per SM: the row gathers of one query are then spread over 32 warps instead
+// of 8, which is what bounds the kernel there — 63 -> ~25 us at 128 queries).
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads, kThreads == 256 ? 6 : 1)
 rescore_kernel(const uint64_t* cand, const uint32_t* cnt, uint32_t cap, uint32_t keep,
                const float* q_f32, int dim, const float* const* seg_f32, uint32_t seg_rows,
                int k, long long id_offset, float* out_scores, long long* out_ids,
