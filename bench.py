@@ -47,8 +47,8 @@ def peaks():
     if os.path.exists(path):
         p = json.load(open(path))
         return dict(bf16=p["bf16_tflops"], bf16_sustained=p.get("bf16_tflops_sustained"), hbm=p["hbm_gbs"],
-                    source="MEASURED_PEAKS.json (of measured)")
-    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback (of fallback)")
+                    source="MEASURED_PEAKS.json (measured on this pool: burst figure; the sustained one is peak_sustained)")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)")
 
 
 class ClockSampler:
@@ -436,10 +436,10 @@ def main():
             "peak_sustained": pk["bf16_sustained"],
             "frac_sustained": achieved / pk["bf16_sustained"] if pk["bf16_sustained"] else None}
     tpath = os.path.join(ROOT, "profiles", "k1_traffic.json")
-    if os.path.exists(tpath):   # dram bytes per corpus row from the committed ncu --set full capture
+    if os.path.exists(tpath):   # dram bytes per corpus row from the committed single-pass ncu metric run
         roof["traffic"] = json.load(open(tpath))["dram_bytes_per_corpus_row"] * n_local
         roof["traffic_unit"] = "bytes per step (sum over the step's K1 launches; ncu dram read+write per row x rows)"
-        roof["traffic_source"] = ("constant from the committed ncu --set full capture (profiles/k1_traffic.json) "
+        roof["traffic_source"] = ("constant from a committed single-pass ncu dram-bytes run over one headline search (profiles/k1_traffic.json) "
                                   "scaled by this rank's rows; NOT measured in this run")
         roof["algorithmic_bytes"] = n_local * DIM * 2 + nq * DIM * 2
     if roof["bound"] == "hbm":
