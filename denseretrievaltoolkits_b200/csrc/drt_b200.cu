@@ -416,7 +416,12 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
     if (cap < 2 * keep) return fail(DRT_E_UNSUPPORTED, "k=%d too large for the candidate buffer", k);
 
     int rc;
-    if ((rc = s->q_bf16.ensure((size_t)nq * dim * 2)) != DRT_OK) return rc;
+    // the 16-bit query plane is padded with zero rows to whole M tiles: a TMA box that hangs over
+    // the end of the tensor is filled with zeros by the copy engine, but measurably slower than a
+    // box it reads (K1 over 8.8M rows: 2.66-2.77 ms at 16 queries against 2.18 ms at 128)
+    const int64_t m_tile_rows = (int64_t)drt::kTileM * std::max(kctas, 1);
+    const int64_t nq_pad = (nq + m_tile_rows - 1) / m_tile_rows * m_tile_rows;
+    if ((rc = s->q_bf16.ensure((size_t)nq_pad * dim * 2)) != DRT_OK) return rc;
     if ((rc = s->thr.ensure((size_t)nq * 4)) != DRT_OK) return rc;
     if ((rc = s->cnt.ensure((size_t)nq * 4)) != DRT_OK) return rc;
     if ((rc = s->cand.ensure((size_t)nq * cap * 8)) != DRT_OK) return rc;
@@ -475,7 +480,11 @@ int search_batch(drt_store* s, const float* q_dev, int64_t nq, int k, float* out
         s->stats[0] += 1;
     }
     CUtensorMap tmap_q;
-    if (!exact_pass && (rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
+    if (!exact_pass) {
+        if (nq_pad > nq)
+            CUDA_TRY(cudaMemsetAsync((char*)s->q_bf16.p + (size_t)nq * dim * 2, 0, (size_t)(nq_pad - nq) * dim * 2, st));
+        if ((rc = make_tmap_bf16(&tmap_q, s->q_bf16.p, (uint64_t)nq_pad, (uint64_t)dim, drt::kTileM)) != DRT_OK) return rc;
+    }
 
     const std::vector<Chunk> chunks = plan_chunks(s->ntotal, s->seg_rows, sel, cap, keep, attempt);
     if (keep_override == 0 && !exact_pass) s->stats[6] = (int64_t)chunks.size();
