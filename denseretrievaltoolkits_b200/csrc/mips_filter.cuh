@@ -95,8 +95,9 @@ __device__ __forceinline__ uint64_t pack_key(float score, uint32_t row) {
 // ub <= thr (the k'-th largest ub), so once the exact k-th score exceeds thr no other row can
 // belong to the top-k: a proof, not an estimate.  K1 works with the 256-row tile maxima
 // (ub_tile >= ub_row: still a bound, a superset is admitted) and stores ub_tile as the
-// candidate's score; for segments in which some tile mixes very different row norms
-// select_kernel tightens the bound to the row's own entry.
+// candidate's score; a tile that mixes very different row norms re-tests its hits against the
+// rows' own entries before admitting them (filter_chunk<true>), and in segments with such tiles
+// select_kernel tightens the stored bound to the row's own entry.
 constexpr float kBoundHuge = 1e30f;     // stands in for non-finite norms (keeps 0 * x finite)
 __device__ __forceinline__ float bound_term(const float4& qb, const float4& rb) {
     return __fmaf_ru(qb.x, rb.x, __fmaf_ru(qb.y, rb.y, __fmul_ru(qb.z, rb.z)));
